@@ -1,0 +1,21 @@
+#!/usr/bin/env bash
+# Builds libdvid_b200.so (sm_100a only) in-tree, plus the oracle's C restatement. Used by __graft_entry__.build().
+set -euo pipefail
+cd "$(dirname "$0")"
+SRC=diffusionvid_b200/csrc
+OUT=diffusionvid_b200/_C
+mkdir -p "$OUT" build
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
+objs=()
+for f in $SRC/*.cu; do
+  o=build/$(basename "${f%.cu}").o
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find $SRC include -name '*.h' -newer "$o" -o -name '*.cuh' -newer "$o")" ]; then
+    echo "nvcc $f"
+    $NVCC $FLAGS -c "$f" -o "$o" &
+  fi
+  objs+=("$o")
+done
+wait
+$NVCC -shared -o "$OUT/libdvid_b200.so" "${objs[@]}"
+echo "built $OUT/libdvid_b200.so"

@@ -1,0 +1,456 @@
+// Implicit-GEMM convolution / GEMM for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+// One persistent, warp-specialised kernel serves every dense contraction on the DiffusionVID hot path:
+//   * backbone convolutions (detectron2 ResNet-101 + FPN restated in SURVEY.md A1; FrozenBN folded into weight/bias),
+//   * every nn.Linear of the decoder (reference mega_core/modeling/roi_heads/box_head/box_head.py:447-491,675-684).
+// Activations are NHWC fp16, weights [Cout][R*S*Cin] fp16 (K-major), accumulation fp32 in TMEM.
+// A GEMM [M,K]x[N,K]^T is the 1x1 "convolution" over an image of height 1 and width M.
+//
+// Tile: 128 output pixels (th x tw patch of one image) x BN output channels, K step 64 channels of one filter tap.
+// The A tile of tap (r,s) is the same 4-D TMA box shifted by (r-pad, s-pad); out-of-bounds rows are zero-filled by
+// TMA, which implements the convolution's zero padding and all tile tails without any predicate in the kernel.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM -> regs -> swizzled smem ->
+// TMA store). Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+#include "ptx_sm100.cuh"
+#include "dvid_internal.h"
+
+namespace dvid {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int OUT_STAGE_BYTES = BLOCK_M * 64 * 2;     // 16 KB, two of them (ping-pong)
+
+struct ConvGemmParams {
+  int n_img, h_out, w_out;
+  int cin, cout;
+  int R, S, pad, stride;
+  int tw_log2, th;  // tile = th x (1 << tw_log2) pixels, th * tw == 128
+  int tiles_x, tiles_y;
+  int m_tiles, n_tiles;
+  int kb_per_tap;    // ceil(cin / 64)
+  int total_kb;      // R * S * kb_per_tap
+  int splits;        // split-K factor (fp32 partial output only)
+  int kb_per_split;  // ceil(total_kb / splits)
+  const float* bias;     // [cout] or nullptr
+  const __half* resid;   // NHWC [n_img, resid_h, resid_w, cout] or nullptr; read at (y >> resid_shift, x >> resid_shift)
+  int resid_shift, resid_h, resid_w;
+  int relu;
+  float* out_f32;        // if set: fp32 output [splits][M][cout] by direct stores (GEMM mode), no bias/resid/relu
+  long long m_total;     // rows of the GEMM view (n_img * h_out * w_out)
+};
+
+template <int BN>
+struct ConvGemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr int SMEM_BYTES =
+      STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
+  uint8_t* sOut = sB + STAGES * Cfg::B_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + 2 * OUT_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int tw = 1 << p.tw_log2;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % p.n_tiles;
+        const int rest = tile / p.n_tiles;
+        const int m_idx = rest % p.m_tiles;
+        const int split = rest / p.m_tiles;
+        const int tx = m_idx % p.tiles_x;
+        const int ty = (m_idx / p.tiles_x) % p.tiles_y;
+        const int img = m_idx / (p.tiles_x * p.tiles_y);
+        const int x_in0 = tx * tw * p.stride - p.pad;
+        const int y_in0 = ty * p.th * p.stride - p.pad;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const int tap = kb / p.kb_per_tap;
+          const int cblk = kb - tap * p.kb_per_tap;
+          const int r = tap / p.S;
+          const int s = tap - r * p.S;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+          tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cblk * BLOCK_K, x_in0 + s, y_in0 + r, img);
+          tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], tap * p.cin + cblk * BLOCK_K,
+                      n_idx * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = (tile / p.n_tiles) / p.m_tiles;
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(sA + stage * A_STAGE_BYTES));
+          const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb_end - 1) umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: the TMEM sub-partition this warp may read
+    const int row = ew * 32 + lane;
+    const bool store_leader = (threadIdx.x == 128);
+    int staged = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_idx = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int m_idx = rest % p.m_tiles;
+      const int split = rest / p.m_tiles;
+      const int tx = m_idx % p.tiles_x;
+      const int ty = (m_idx / p.tiles_x) % p.tiles_y;
+      const int img = m_idx / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * tw, y0 = ty * p.th;
+      const int x = x0 + (row & (tw - 1));
+      const int y = y0 + (row >> p.tw_log2);
+      const bool valid = (x < p.w_out) && (y < p.h_out);
+
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+
+      if (p.out_f32 != nullptr) {
+        // split-K partials: fp32, direct vector stores (GEMM view: th == 1, row index = x)
+        float* dst = p.out_f32 + (static_cast<long long>(split) * p.m_total + x) * p.cout;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int ch0 = n_idx * BN + c * 32;
+          if (ch0 >= p.cout) break;
+          uint32_t v[32];
+          tmem_ld32(tbase + c * 32, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (ch0 + q * 4 < p.cout) {
+                float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                *reinterpret_cast<float4*>(dst + ch0 + q * 4) = o;
+              }
+            }
+          }
+        }
+      } else {
+        long long resid_off = 0;
+        if (p.resid != nullptr && valid) {
+          resid_off = ((static_cast<long long>(img) * p.resid_h + (y >> p.resid_shift)) * p.resid_w +
+                       (x >> p.resid_shift)) * p.cout;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int ch0 = n_idx * BN + c * 64;
+          if (ch0 >= p.cout) break;
+          uint8_t* buf = sOut + (staged & 1) * OUT_STAGE_BYTES;
+          if (store_leader) tma_store_wait_read<1>();  // the store that last read this buffer has drained it
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld32(tbase + c * 64 + h * 32, v);
+            tmem_ld_wait();
+            const int chh = ch0 + h * 32;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (chh + j < p.cout) f[j] += __ldg(p.bias + chh + j);
+            }
+            if (p.resid != nullptr && valid) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (chh + q * 8 < p.cout) {
+                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.resid + resid_off + chh + q * 8));
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 rf = __half22float2(rh[e]);
+                    f[q * 8 + 2 * e] += rf.x;
+                    f[q * 8 + 2 * e + 1] += rf.y;
+                  }
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 pk;
+              pk.x = pack_half2(f[q * 8 + 0], f[q * 8 + 1]);
+              pk.y = pack_half2(f[q * 8 + 2], f[q * 8 + 3]);
+              pk.z = pack_half2(f[q * 8 + 4], f[q * 8 + 5]);
+              pk.w = pack_half2(f[q * 8 + 6], f[q * 8 + 7]);
+              const int chunk = h * 4 + q;  // 16-byte chunk inside the 128-byte row
+              *reinterpret_cast<uint4*>(buf + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (store_leader) {
+            tma_store_4d(&tmC, buf, ch0, x0, y0, img);
+            tma_store_commit();
+          }
+          ++staged;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (store_leader) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// fp16 tensor map, 128-byte swizzle, dims innermost-first. Returns 0 on success.
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, const uint32_t* elem_strides) {
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) return DVID_ERR_DRIVER;
+  cuuint64_t gdim[5];
+  cuuint64_t gstride[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = elem_strides ? elem_strides[i] : 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "dvid: cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,...] box=[%u,%u,...]\n", (int)r,
+            rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0],
+            rank > 1 ? box[1] : 0);
+    return DVID_ERR_DRIVER;
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p,
+                      cudaStream_t stream) {
+  using Cfg = ConvGemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return DVID_ERR_CUDA;
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  conv_gemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
+}
+
+// in: NHWC fp16 [n,h,w,cin]; weight: [cout][R*S*cin] fp16; out: NHWC fp16 [n,h_out,w_out,cout] (or out_f32 partials).
+int conv_gemm_launch(const void* in, const void* weight, const float* bias, const void* resid, void* out,
+                     float* out_f32, int n, int h, int w, int cin, int cout, int R, int S, int stride, int pad,
+                     int resid_shift, int relu, int splits, int force_bn, cudaStream_t stream) {
+  if (cin % 8 != 0 || cout % 8 != 0) return DVID_ERR_SHAPE;
+  if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return DVID_ERR_SHAPE;
+  if (stride < 1 || stride > 2) return DVID_ERR_SHAPE;
+  ConvGemmParams p;
+  p.n_img = n;
+  p.h_out = (h + 2 * pad - R) / stride + 1;
+  p.w_out = (w + 2 * pad - S) / stride + 1;
+  if (p.h_out <= 0 || p.w_out <= 0) return DVID_ERR_SHAPE;
+  p.cin = cin;
+  p.cout = cout;
+  p.R = R; p.S = S; p.pad = pad; p.stride = stride;
+  // choose the th x tw pixel patch (tw power of two, th*tw = 128) that covers the image with fewest tiles
+  int best_log2 = 7;
+  long long best_tiles = -1;
+  for (int l2 = 7; l2 >= 0; --l2) {
+    const int tw = 1 << l2, th = 128 >> l2;
+    if (stride > 1 && (tw * stride > 256 || th * stride > 256)) continue;
+    const long long t = static_cast<long long>((p.w_out + tw - 1) / tw) * ((p.h_out + th - 1) / th);
+    if (best_tiles < 0 || t < best_tiles) { best_tiles = t; best_log2 = l2; }
+  }
+  if (best_tiles < 0) return DVID_ERR_SHAPE;
+  p.tw_log2 = best_log2;
+  p.th = 128 >> best_log2;
+  const int tw = 1 << best_log2;
+  p.tiles_x = (p.w_out + tw - 1) / tw;
+  p.tiles_y = (p.h_out + p.th - 1) / p.th;
+  p.m_tiles = n * p.tiles_x * p.tiles_y;
+  p.kb_per_tap = (cin + BLOCK_K - 1) / BLOCK_K;
+  p.total_kb = R * S * p.kb_per_tap;
+  if (out_f32 == nullptr) splits = 1;
+  if (splits < 1) splits = 1;
+  if (splits > p.total_kb) splits = p.total_kb;
+  p.kb_per_split = (p.total_kb + splits - 1) / splits;
+  p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  p.bias = bias;
+  p.resid = reinterpret_cast<const __half*>(resid);
+  p.resid_shift = resid_shift;
+  p.resid_h = ((p.h_out - 1) >> resid_shift) + 1;
+  p.resid_w = ((p.w_out - 1) >> resid_shift) + 1;
+  p.relu = relu;
+  p.out_f32 = out_f32;
+  p.m_total = static_cast<long long>(n) * p.h_out * p.w_out;
+  if (out_f32 != nullptr && !(p.h_out == 1 && n == 1 && p.th == 1)) return DVID_ERR_SHAPE;  // GEMM view only
+
+  int bn = force_bn;
+  if (bn == 0) {
+    const long long want = (num_sms() * 4) / 5;
+    if (cout >= 256 && static_cast<long long>(p.m_tiles) * p.splits * ((cout + 255) / 256) >= want) bn = 256;
+    else if (cout >= 128 && static_cast<long long>(p.m_tiles) * p.splits * ((cout + 127) / 128) >= want) bn = 128;
+    else bn = (cout >= 256 && p.m_tiles * p.splits >= 16) ? 128 : 64;
+    if (cout <= 64) bn = 64;
+  }
+  if (bn != 64 && bn != 128 && bn != 256) return DVID_ERR_SHAPE;
+  p.n_tiles = (cout + bn - 1) / bn;
+
+  CUtensorMap tmA, tmB, tmC;
+  {
+    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(tw * stride), (uint32_t)(p.th * stride), 1};
+    const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int r = make_tmap_f16(&tmA, in, 4, dims, strides, box, es);
+    if (r) return r;
+  }
+  {
+    const uint64_t ktot = (uint64_t)R * S * cin;
+    const uint64_t dims[2] = {ktot, (uint64_t)cout};
+    const uint64_t strides[1] = {ktot * 2};
+    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)bn};
+    int r = make_tmap_f16(&tmB, weight, 2, dims, strides, box, nullptr);
+    if (r) return r;
+  }
+  if (out != nullptr) {
+    const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)p.w_out, (uint64_t)p.h_out, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cout * 2, (uint64_t)p.w_out * cout * 2,
+                                 (uint64_t)p.h_out * p.w_out * cout * 2};
+    const uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)p.th, 1};
+    int r = make_tmap_f16(&tmC, out, 4, dims, strides, box, nullptr);
+    if (r) return r;
+  } else {
+    if (out_f32 == nullptr) return DVID_ERR_SHAPE;
+    tmC = tmA;  // unused by the fp32 path
+  }
+  if (bn == 256) return launch_cfg<256>(tmA, tmB, tmC, p, stream);
+  if (bn == 128) return launch_cfg<128>(tmA, tmB, tmC, p, stream);
+  return launch_cfg<64>(tmA, tmB, tmC, p, stream);
+}
+
+}  // namespace dvid
