@@ -6,7 +6,7 @@ SRC=diffusionvid_b200/csrc
 OUT=diffusionvid_b200/_C
 mkdir -p "$OUT" build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
+FLAGS="-Xptxas -v -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
 objs=()
 for f in $SRC/*.cu; do
   o=build/$(basename "${f%.cu}").o

@@ -13,6 +13,37 @@ ERRORS = {1: "DVID_ERR_SHAPE", 2: "DVID_ERR_CUDA", 3: "DVID_ERR_DRIVER", 4: "DVI
 
 _lib = None
 
+P = ctypes.c_void_p
+I = ctypes.c_int
+L = ctypes.c_long
+F = ctypes.c_float
+
+# name -> argtypes; every entry point returns int.  Kept in the order of include/dvid_b200.h.
+SIGNATURES = {
+    "dvid_abi_version": [],
+    "dvid_num_sms": [],
+    "dvid_conv2d_nhwc_f16": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "dvid_stem_conv_f16": [P, P, P, P, I, I, I, I, I, P],
+    "dvid_gemm_f16": [P, P, P, P, P, P, I, I, I, I, I, P, P],
+    "dvid_preprocess": [P, P, I, I, I, I, I, I, P, P, P],
+    "dvid_maxpool3x3s2_nhwc_f16": [P, P, I, I, I, I, P],
+    "dvid_attention_hd32": [P, P, P, P, I, I, I, I, L, L, L, L, L, L, L, L, P],
+    "dvid_roi_align": [P, P, P, P, P, I, I, P, P, P, P],
+    "dvid_roi_dynconv": [P, P, P, P, P, I, I, P, P, P, P, P, P, P, P],
+    "dvid_row_post": [P, I, L, P, P, P, P, I, P, P, P, I, I, P, P, P, P, I, I, I, I, P, I, P],
+    "dvid_small_linear": [P, P, P, P, I, I, I, I, I, P],
+    "dvid_time_sinusoid": [P, P, P, I, P],
+    "dvid_head_final": [P, I, P, I, P, I, P, P, P, P, I, P],
+    "dvid_noise_to_boxes": [P, P, I, F, F, F, P],
+    "dvid_ddim_step": [P, I, P, P, P, P, P, P, P, I, I, F, F, F, F, F, F, F, F, P],
+    "dvid_topk_scores": [P, P, I, I, I, I, P, P, P, I, I, P],
+    "dvid_topk_mask": [P, I, I, I, I, I, P, P, P],
+    "dvid_gather_masked_rows": [P, P, I, I, I, P, P],
+    "dvid_nms": [P, P, P, P, I, I, I, F, I, I, I, F, F, P, P, P, P, P, P],
+    "dvid_cdist_f32": [P, P, I, I, P],
+    "dvid_furthest_point_sampling": [I, I, I, P, P, P, P],
+}
+
 
 class DvidError(RuntimeError):
     pass
@@ -26,7 +57,12 @@ def lib():
             raise DvidError(
                 f"{LIB_PATH} not found: build it with ./build.sh (or __graft_entry__.build()). "
                 "diffusionvid_b200 has no fallback path.")
-        _lib = ctypes.CDLL(LIB_PATH)
+        cdll = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(cdll, name)      # AttributeError here = header / library mismatch: fail loudly
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+        _lib = cdll
     return _lib
 
 
@@ -38,7 +74,7 @@ def check(code, what):
 def ptr(t):
     """Device pointer of a torch tensor (or None) as c_void_p."""
     if t is None:
-        return ctypes.c_void_p(0)
+        return None
     return ctypes.c_void_p(t.data_ptr())
 
 

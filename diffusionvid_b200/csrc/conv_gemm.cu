@@ -364,7 +364,8 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 // in: NHWC fp16 [n,h,w,cin]; weight: [cout][R*S*cin] fp16; out: NHWC fp16 [n,h_out,w_out,cout] (or out_f32 partials).
 int conv_gemm_launch(const void* in, const void* weight, const float* bias, const void* resid, void* out,
                      float* out_f32, int n, int h, int w, int cin, int cout, int R, int S, int stride, int pad,
-                     int resid_shift, int relu, int splits, int force_bn, cudaStream_t stream) {
+                     int resid_shift, int relu, int splits, int force_bn, cudaStream_t stream,
+                     const uint64_t* a_strides_bytes) {
   if (cin % 8 != 0 || cout % 8 != 0) return DVID_ERR_SHAPE;
   if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return DVID_ERR_SHAPE;
   if (stride < 1 || stride > 2) return DVID_ERR_SHAPE;
@@ -423,7 +424,10 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   CUtensorMap tmA, tmB, tmC;
   {
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-    const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+    uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+    if (a_strides_bytes != nullptr) {   // overlapping-window view (stem convolution), see stem_conv_launch
+      for (int i = 0; i < 3; ++i) strides[i] = a_strides_bytes[i];
+    }
     const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(tw * stride), (uint32_t)(p.th * stride), 1};
     const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     int r = make_tmap_f16(&tmA, in, 4, dims, strides, box, es);
@@ -451,6 +455,21 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   if (bn == 256) return launch_cfg<256>(tmA, tmB, tmC, p, stream);
   if (bn == 128) return launch_cfg<128>(tmA, tmB, tmC, p, stream);
   return launch_cfg<64>(tmA, tmB, tmC, p, stream);
+}
+
+// Stem convolution 7x7 / stride 2 / pad 3 with 3 input channels (detectron2 BasicStem) as an implicit
+// GEMM without im2col.  Input: the zero-haloed NHWC8 image written by preprocess_launch, [n][H+6][W+6][8] fp16
+// (3 real channels).  A TMA view with OVERLAPPING rows exposes, for every pixel x of a padded row, the 64 contiguous
+// fp16 = 8 pixels x 8 channels starting there: dims {64, W-1, H+6, n}, strides {16 B, (W+6)*16 B, ...}.  One filter
+// row (r) is then a K=64 block, so the 7x7x3 filter becomes a 7x1 "convolution" over a 64-channel virtual image
+// with the weights laid out [cout][r][s(8, last zero)][c(8, last five zero)].
+int stem_conv_launch(const void* in_haloed, const void* weight, const float* bias, void* out, int n, int H, int W,
+                     int cout, int relu, cudaStream_t stream) {
+  if (H % 2 != 0 || W % 2 != 0 || H < 8 || W < 8) return DVID_ERR_SHAPE;
+  const uint64_t wp = (uint64_t)W + 6, hp = (uint64_t)H + 6;
+  const uint64_t strides[3] = {16, wp * 16, hp * wp * 16};
+  return conv_gemm_launch(in_haloed, weight, bias, nullptr, out, nullptr, n, H + 6, W - 1, 64, cout, 7, 1, 2, 0, 0, relu,
+                          1, 0, stream, strides);
 }
 
 }  // namespace dvid

@@ -19,7 +19,55 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 
 int conv_gemm_launch(const void* in, const void* weight, const float* bias, const void* resid, void* out,
                      float* out_f32, int n, int h, int w, int cin, int cout, int R, int S, int stride, int pad,
-                     int resid_shift, int relu, int splits, int force_bn, cudaStream_t stream);
+                     int resid_shift, int relu, int splits, int force_bn, cudaStream_t stream,
+                     const uint64_t* a_strides_bytes = nullptr);
+int stem_conv_launch(const void* in_haloed, const void* weight, const float* bias, void* out, int n, int H, int W,
+                     int cout, int relu, cudaStream_t stream);
+
+int attention_launch(const void* q, const void* k, const void* v, void* o, int batch, int heads, int lq, int lk,
+                     long q_rs, long k_rs, long v_rs, long o_rs, long q_bs, long k_bs, long v_bs, long o_bs,
+                     cudaStream_t stream);
+
+int roi_align_launch(const void* const* feats, const int* hs, const int* ws, const float* scales, const float* boxes,
+                     int num_boxes, int boxes_per_frame, void* roi_out, float* mean_f32, void* mean_f16,
+                     cudaStream_t stream);
+int roi_dynconv_launch(const void* const* feats, const int* hs, const int* ws, const float* scales,
+                       const float* boxes, int num_boxes, int boxes_per_frame, const void* roi_in, const void* params,
+                       const float* g1, const float* b1, const float* g2, const float* b2, void* out,
+                       cudaStream_t stream);
+
+int preprocess_launch(const float* img, void* out, int n, int H, int W, int halo, int Hp, int Wp, const float* mean,
+                      const float* std, cudaStream_t stream);
+int maxpool_launch(const void* in, void* out, int n, int H, int W, int C, cudaStream_t stream);
+int row_post_launch(const float* partials, int splits, long split_stride, const void* in_f16, const float* bias,
+                    const float* ln1_g, const float* ln1_b, int relu1, const float* resid, const float* ln2_g,
+                    const float* ln2_b, int act2, int act2_f16_only, float* out_f32, void* out_f16,
+                    const float* mod_scale, const float* mod_shift, int rows_per_group, int scale_stride,
+                    int shift_stride, int shift_per_row, void* out_mod_f16, int M, cudaStream_t stream);
+int small_linear_launch(const float* a, const void* w, const float* bias, float* out, int m, int n, int k, int act_in,
+                        int act_out, cudaStream_t stream);
+int time_sinusoid_launch(const float* t, const float* freq, float* out, int m, cudaStream_t stream);
+int head_final_launch(const float* logit_part, int ldl, const float* cls_bias, int C, const float* delta_part, int ldd,
+                      const float* delta_bias, const float* boxes_in, float* logits_out, float* boxes_out, int M,
+                      cudaStream_t stream);
+int noise_to_boxes_launch(const float* x, float* boxes, int M, float scale, float W, float H, cudaStream_t stream);
+int ddim_step_launch(const float* logits, int C, const float* coord, const float* x_t, const float* eps,
+                     const float* fill, float* x_next, float* boxes_next, int* num_kept, int frames, int N,
+                     float scale, float W, float H, float sqrt_recip_a, float sqrt_recipm1_a, float sqrt_a_next,
+                     float c_coef, float sigma, cudaStream_t stream);
+
+int topk_scores_launch(const float* logits, const float* boxes, int frames, int N, int C, int k, float* out_boxes,
+                       float* out_scores, int* out_labels, int cap, int slot0, cudaStream_t stream);
+int topk_mask_launch(const float* logits, int frames, int N, int C, int k1, int k2, unsigned char* mask1,
+                     unsigned char* mask2, cudaStream_t stream);
+int gather_masked_rows_launch(const float* src, const unsigned char* mask, int frames, int N, int k, float* dst,
+                              cudaStream_t stream);
+int nms_launch(const float* boxes, const float* scores, const int* labels, const int* counts, int n, int cap,
+               int frames, float thr, int plus_one, int ge, int ascending_out, float clip_w, float clip_h,
+               long long* keep_idx, float* out_boxes, float* out_scores, int* out_labels, int* out_count,
+               cudaStream_t stream);
+int cdist_launch(const float* x, float* out, int n, int d, cudaStream_t stream);
+int fps_launch(int b, int n, int m, const float* dist, float* temp, int* idx, cudaStream_t stream);
 
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? DVID_OK : DVID_ERR_CUDA; }
 

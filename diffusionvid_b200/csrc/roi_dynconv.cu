@@ -1,0 +1,444 @@
+// Multi-level ROIAlign + DynamicConv instance interaction, one CTA per box.
+//
+// Replaces, for every box of every frame of a DDIM step:
+//   * detectron2 ROIPooler -> torchvision roi_align(aligned=True, 7x7, sampling_ratio 2) over the p3/p4/p5 maps
+//     (call sites mega_core/modeling/roi_heads/box_head/box_head.py:507,617; level rule SURVEY.md A2/A3)
+//   * DynamicConv.forward's two per-box bmm's with their LayerNorm+ReLU (box_head.py:698-704)
+// Feature maps are NHWC fp16 (256 channels = one 512-byte vector per tap, read by one warp as 32 x 16 B), so the
+// data-dependent bilinear gather is fully coalesced.  The 7x7x256 ROI tile, the box's generated 256x64 / 64x256
+// weights (fp16, produced by the tcgen05 `dynamic_layer` GEMM) and the 49x64 intermediate all live in shared memory;
+// only the final 49x256 fp16 activations go back to HBM (they feed the K=12544 `out_layer` tcgen05 GEMM).
+//
+// Two kernels share the gather code:
+//   roi_align_kernel      : ROI tile -> global (and the per-box mean that seeds pro_features, box_head.py:509-510)
+//   roi_dynconv_kernel<G> : G=false gathers the ROI tile itself (fused ROIAlign), G=true reads it from global.
+#include "dvid_internal.h"
+#include "warp_mma.cuh"
+
+namespace dvid {
+
+namespace {
+
+constexpr int D = 256;     // hidden dim / feature channels
+constexpr int DD = 64;     // dynamic dim
+constexpr int P = 7;       // pooler resolution
+constexpr int NBIN = P * P;
+
+struct RoiLevels {
+  const __half* feat[3];   // NHWC fp16 [frames][H_l][W_l][256]
+  int h[3], w[3];
+  float scale[3];
+};
+
+// ---- shared-memory layouts (all fp16, 16-byte chunks XOR-swizzled by row&7 so ldmatrix phases are conflict-free)
+__device__ __forceinline__ uint32_t off512(int row, int chunk) {   // rows of 256 halfs (32 chunks)
+  return static_cast<uint32_t>(row * 512 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ uint32_t off128(int row, int chunk) {   // rows of 64 halfs (8 chunks)
+  return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// One axis of the 2-sample bilinear footprint of a bin: up to 4 (index, weight) taps, duplicates merged.
+struct AxisTaps {
+  int idx[4];
+  float w[4];
+};
+
+// torchvision bilinear_interpolate semantics along one axis: sample invalid if v < -1 or v > size;
+// clamp to >= 0; low = (int)v; if low >= size-1 -> low = high = size-1, v = low.
+__device__ __forceinline__ void axis_taps(float start, float bin, int pbin, int size, AxisTaps& a) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    // y = roi_start + ph*bin + (iy + .5) * bin / 2
+    float v = __fadd_rn(__fadd_rn(start, __fmul_rn(static_cast<float>(pbin), bin)),
+                        __fdiv_rn(__fmul_rn(static_cast<float>(i) + 0.5f, bin), 2.0f));
+    const bool bad = (v < -1.0f) || (v > static_cast<float>(size));
+    v = fmaxf(v, 0.f);
+    int lo = static_cast<int>(v);
+    int hi;
+    if (lo >= size - 1) {
+      lo = hi = size - 1;
+      v = static_cast<float>(lo);
+    } else {
+      hi = lo + 1;
+    }
+    const float l = v - static_cast<float>(lo);
+    const float h = 1.0f - l;
+    a.idx[2 * i] = lo;
+    a.w[2 * i] = bad ? 0.f : h;
+    a.idx[2 * i + 1] = hi;
+    a.w[2 * i + 1] = bad ? 0.f : l;
+  }
+  // merge duplicate indices (adjacent samples of a small bin share taps)
+#pragma unroll
+  for (int i = 1; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      if (a.idx[i] == a.idx[j] && a.w[i] != 0.f) {
+        a.w[j] += a.w[i];
+        a.w[i] = 0.f;
+      }
+    }
+  }
+}
+
+struct RoiGeom {
+  const __half* feat;   // frame base
+  int H, W;
+  float x1, y1, bw, bh;
+};
+
+// Level assignment (detectron2 assign_boxes_to_levels) + aligned ROI geometry for box `b`.
+__device__ __forceinline__ RoiGeom roi_geometry(const RoiLevels& lv, const float* __restrict__ boxes, int b,
+                                               int boxes_per_frame) {
+  const float4 bx = __ldg(reinterpret_cast<const float4*>(boxes) + b);
+  const float area = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+  const float size = sqrtf(area);
+  float lf = floorf(__fadd_rn(4.0f, log2f(__fadd_rn(__fdiv_rn(size, 224.0f), 1e-8f))));
+  // NaN (negative area) compares false everywhere -> clamp to the lowest level like torch.clamp(min) then long cast
+  int l = (lf >= 5.0f) ? 2 : ((lf >= 4.0f) ? 1 : 0);
+  const int frame = b / boxes_per_frame;
+  RoiGeom gm;
+  gm.H = lv.h[l];
+  gm.W = lv.w[l];
+  gm.feat = lv.feat[l] + static_cast<long>(frame) * gm.H * gm.W * D;
+  const float sc = lv.scale[l];
+  gm.x1 = __fsub_rn(__fmul_rn(bx.x, sc), 0.5f);
+  gm.y1 = __fsub_rn(__fmul_rn(bx.y, sc), 0.5f);
+  const float x2 = __fsub_rn(__fmul_rn(bx.z, sc), 0.5f);
+  const float y2 = __fsub_rn(__fmul_rn(bx.w, sc), 0.5f);
+  gm.bw = __fdiv_rn(__fsub_rn(x2, gm.x1), static_cast<float>(P));
+  gm.bh = __fdiv_rn(__fsub_rn(y2, gm.y1), static_cast<float>(P));
+  return gm;
+}
+
+// Gather one 7x7 bin (all 256 channels) with the calling warp: lane owns channels [8*lane, 8*lane+8).
+__device__ __forceinline__ void roi_bin(const RoiGeom& gm, int bin, int lane, float (&acc)[8]) {
+  const int ph = bin / P, pw = bin - ph * P;
+  AxisTaps ty, tx;
+  axis_taps(gm.y1, gm.bh, ph, gm.H, ty);
+  axis_taps(gm.x1, gm.bw, pw, gm.W, tx);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int iy = 0; iy < 4; ++iy) {
+    if (ty.w[iy] == 0.f) continue;   // warp-uniform
+    const __half* rowp = gm.feat + static_cast<long>(ty.idx[iy]) * gm.W * D + lane * 8;
+    uint4 v[4];
+#pragma unroll
+    for (int ix = 0; ix < 4; ++ix) {
+      if (tx.w[ix] != 0.f) v[ix] = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long>(tx.idx[ix]) * D));
+    }
+#pragma unroll
+    for (int ix = 0; ix < 4; ++ix) {
+      if (tx.w[ix] != 0.f) {
+        const float wgt = ty.w[iy] * tx.w[ix];
+        const __half2* hp = reinterpret_cast<const __half2*>(&v[ix]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(hp[e]);
+          acc[2 * e] = fmaf(wgt, f.x, acc[2 * e]);
+          acc[2 * e + 1] = fmaf(wgt, f.y, acc[2 * e + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] *= 0.25f;   // mean of the 2x2 samples
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&a)[8]) {
+  uint4 r;
+  r.x = pack2h(a[0], a[1]);
+  r.y = pack2h(a[2], a[3]);
+  r.z = pack2h(a[4], a[5]);
+  r.w = pack2h(a[6], a[7]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------ ROIAlign only
+__global__ void __launch_bounds__(256)
+roi_align_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_frame, __half* __restrict__ roi_out,
+                 float* __restrict__ mean_f32, __half* __restrict__ mean_f16) {
+  __shared__ float sred[8][D];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RoiGeom gm = roi_geometry(lv, boxes, b, boxes_per_frame);
+  float msum[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) msum[e] = 0.f;
+  for (int bin = warp; bin < NBIN; bin += 8) {
+    float acc[8];
+    roi_bin(gm, bin, lane, acc);
+    const uint4 pk = pack8(acc);
+    if (roi_out) *reinterpret_cast<uint4*>(roi_out + (static_cast<long>(b) * NBIN + bin) * D + lane * 8) = pk;
+    const __half2* hp = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {   // the mean is taken over the fp16-rounded values that downstream code sees
+      const float2 f = __half22float2(hp[e]);
+      msum[2 * e] += f.x;
+      msum[2 * e + 1] += f.y;
+    }
+  }
+  if (mean_f32 == nullptr && mean_f16 == nullptr) return;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sred[warp][lane * 8 + e] = msum[e];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += sred[w][c];
+  s = __fdiv_rn(s, static_cast<float>(NBIN));
+  if (mean_f32) mean_f32[static_cast<long>(b) * D + c] = s;
+  if (mean_f16) mean_f16[static_cast<long>(b) * D + c] = __float2half_rn(s);
+}
+
+// ------------------------------------------------------------------------------------------------ fused DynamicConv
+constexpr int SM_ROI = 0;                   // 64 x 512 B (rows 49..63 zero); reused as the output staging tile
+constexpr int SM_P1 = SM_ROI + 64 * 512;    // 256 x 128 B
+constexpr int SM_P2 = SM_P1 + 256 * 128;    // 64 x 512 B
+constexpr int SM_F1 = SM_P2 + 64 * 512;     // 64 x 128 B
+constexpr int SM_STAT = SM_F1 + 64 * 128;   // 64 x 2 floats
+constexpr int SM_TOTAL = SM_STAT + 64 * 2 * 4;
+
+// LayerNorm statistics of rows split across the two warps (nh = 0/1) that share a 16-row slab.
+// part[h] = this thread's partial for row g + 8h; returns the full-row sum for both rows.
+__device__ __forceinline__ void row_allreduce(float (&part)[2], float* sstat, int row0, int g, int t, int nh) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) part[h] = quad_sum(part[h]);
+  __syncthreads();   // previous users of sstat are done
+  if (t == 0) {
+    sstat[(row0 + g) * 2 + nh] = part[0];
+    sstat[(row0 + g + 8) * 2 + nh] = part[1];
+  }
+  __syncthreads();
+  part[0] = sstat[(row0 + g) * 2] + sstat[(row0 + g) * 2 + 1];
+  part[1] = sstat[(row0 + g + 8) * 2] + sstat[(row0 + g + 8) * 2 + 1];
+}
+
+template <bool kRoiFromGlobal>
+__global__ void __launch_bounds__(256, 2)
+roi_dynconv_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_frame,
+                   const __half* __restrict__ roi_in,      // [M][49][256] (kRoiFromGlobal)
+                   const __half* __restrict__ params,      // [M][2*256*64]: P1 [256][64] then P2 [64][256]
+                   const float* __restrict__ g1, const float* __restrict__ b1,   // LayerNorm(64)
+                   const float* __restrict__ g2, const float* __restrict__ b2,   // LayerNorm(256)
+                   __half* __restrict__ out) {              // [M][49][256]
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sRoi = smem + SM_ROI;
+  uint8_t* sP1 = smem + SM_P1;
+  uint8_t* sP2 = smem + SM_P2;
+  uint8_t* sF1 = smem + SM_F1;
+  float* sStat = reinterpret_cast<float*>(smem + SM_STAT);
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- async loads of the box's generated weights (and ROI tile when it comes from global)
+  {
+    const __half* p1 = params + static_cast<long>(b) * (2 * D * DD);
+    const __half* p2 = p1 + D * DD;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int id = tid + i * 256;            // 2048 chunks: [256 rows][8 chunks]
+      cp_async16(sP1 + off128(id >> 3, id & 7), p1 + id * 8, true);
+    }
+    if (kRoiFromGlobal) {
+      const __half* r = roi_in + static_cast<long>(b) * NBIN * D;
+      for (int id = tid; id < NBIN * 32; id += 256) cp_async16(sRoi + off512(id >> 5, id & 31), r + id * 8, true);
+    }
+    cp_async_commit();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int id = tid + i * 256;            // 2048 chunks: [64 rows][32 chunks]
+      cp_async16(sP2 + off512(id >> 5, id & 31), p2 + id * 8, true);
+    }
+    cp_async_commit();
+  }
+  // zero the padding rows 49..63 of the ROI tile
+  for (int id = tid; id < (64 - NBIN) * 32; id += 256)
+    *reinterpret_cast<uint4*>(sRoi + off512(NBIN + (id >> 5), id & 31)) = make_uint4(0, 0, 0, 0);
+
+  if (!kRoiFromGlobal) {
+    const RoiGeom gm = roi_geometry(lv, boxes, b, boxes_per_frame);
+    for (int bin = warp; bin < NBIN; bin += 8) {
+      float acc[8];
+      roi_bin(gm, bin, lane, acc);
+      *reinterpret_cast<uint4*>(sRoi + off512(bin, lane)) = pack8(acc);
+    }
+  }
+  cp_async_wait<1>();   // P1 (+ROI) landed
+  __syncthreads();
+
+  const int mt = warp & 3;    // 16-row slab
+  const int nh = warp >> 2;   // column half
+  const int lj = lane >> 3, lr = lane & 7;
+
+  // ---- bmm1: F1[64x64] = ROI[64x256] @ P1[256x64]; this warp: rows mt*16.., cols nh*32..+31
+  float acc1[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc1[i][j] = 0.f;
+#pragma unroll 4
+  for (int ks = 0; ks < D / 16; ++ks) {
+    uint32_t a[4];
+    ldmatrix_x4(a, smem_addr(sRoi + off512(mt * 16 + (lj & 1) * 8 + lr, ks * 2 + (lj >> 1))));
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bb[4];
+      ldmatrix_x4_trans(bb, smem_addr(sP1 + off128(ks * 16 + (lj & 1) * 8 + lr, nh * 4 + np * 2 + (lj >> 1))));
+      mma_16816(acc1[np * 2], a, bb[0], bb[1]);
+      mma_16816(acc1[np * 2 + 1], a, bb[2], bb[3]);
+    }
+  }
+  // LayerNorm(64) + ReLU -> sF1 (fp16)
+  {
+    float part[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      part[0] += acc1[i][0] + acc1[i][1];
+      part[1] += acc1[i][2] + acc1[i][3];
+    }
+    row_allreduce(part, sStat, mt * 16, g, t, nh);
+    const float mean0 = part[0] * (1.f / DD), mean1 = part[1] * (1.f / DD);
+    part[0] = part[1] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float d0 = acc1[i][0] - mean0, d1 = acc1[i][1] - mean0, d2 = acc1[i][2] - mean1, d3 = acc1[i][3] - mean1;
+      part[0] += d0 * d0 + d1 * d1;
+      part[1] += d2 * d2 + d3 * d3;
+    }
+    row_allreduce(part, sStat, mt * 16, g, t, nh);
+    const float rstd0 = rsqrtf(part[0] * (1.f / DD) + 1e-5f), rstd1 = rsqrtf(part[1] * (1.f / DD) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = nh * 32 + i * 8 + 2 * t;
+      const float2 gg = __ldg(reinterpret_cast<const float2*>(g1 + col));
+      const float2 be = __ldg(reinterpret_cast<const float2*>(b1 + col));
+      const float y0 = fmaxf((acc1[i][0] - mean0) * rstd0 * gg.x + be.x, 0.f);
+      const float y1 = fmaxf((acc1[i][1] - mean0) * rstd0 * gg.y + be.y, 0.f);
+      const float y2 = fmaxf((acc1[i][2] - mean1) * rstd1 * gg.x + be.x, 0.f);
+      const float y3 = fmaxf((acc1[i][3] - mean1) * rstd1 * gg.y + be.y, 0.f);
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      *reinterpret_cast<uint32_t*>(sF1 + off128(r0, col >> 3) + (col & 7) * 2) = pack2h(y0, y1);
+      *reinterpret_cast<uint32_t*>(sF1 + off128(r1, col >> 3) + (col & 7) * 2) = pack2h(y2, y3);
+    }
+  }
+  cp_async_wait<0>();   // P2 landed
+  __syncthreads();      // sF1 complete; all warps finished reading sRoi
+
+  // ---- bmm2: F2[64x256] = F1[64x64] @ P2[64x256]; this warp: rows mt*16.., cols nh*128..+127
+  float acc2[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc2[i][j] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < DD / 16; ++ks) {
+    uint32_t a[4];
+    ldmatrix_x4(a, smem_addr(sF1 + off128(mt * 16 + (lj & 1) * 8 + lr, ks * 2 + (lj >> 1))));
+#pragma unroll
+    for (int np = 0; np < 8; ++np) {
+      uint32_t bb[4];
+      ldmatrix_x4_trans(bb, smem_addr(sP2 + off512(ks * 16 + (lj & 1) * 8 + lr, nh * 16 + np * 2 + (lj >> 1))));
+      mma_16816(acc2[np * 2], a, bb[0], bb[1]);
+      mma_16816(acc2[np * 2 + 1], a, bb[2], bb[3]);
+    }
+  }
+  // LayerNorm(256) + ReLU -> staging tile (reuses sRoi) -> global
+  {
+    float part[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      part[0] += acc2[i][0] + acc2[i][1];
+      part[1] += acc2[i][2] + acc2[i][3];
+    }
+    row_allreduce(part, sStat, mt * 16, g, t, nh);
+    const float mean0 = part[0] * (1.f / D), mean1 = part[1] * (1.f / D);
+    part[0] = part[1] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float d0 = acc2[i][0] - mean0, d1 = acc2[i][1] - mean0, d2 = acc2[i][2] - mean1, d3 = acc2[i][3] - mean1;
+      part[0] += d0 * d0 + d1 * d1;
+      part[1] += d2 * d2 + d3 * d3;
+    }
+    row_allreduce(part, sStat, mt * 16, g, t, nh);
+    const float rstd0 = rsqrtf(part[0] * (1.f / D) + 1e-5f), rstd1 = rsqrtf(part[1] * (1.f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = nh * 128 + i * 8 + 2 * t;
+      const float2 gg = __ldg(reinterpret_cast<const float2*>(g2 + col));
+      const float2 be = __ldg(reinterpret_cast<const float2*>(b2 + col));
+      const float y0 = fmaxf((acc2[i][0] - mean0) * rstd0 * gg.x + be.x, 0.f);
+      const float y1 = fmaxf((acc2[i][1] - mean0) * rstd0 * gg.y + be.y, 0.f);
+      const float y2 = fmaxf((acc2[i][2] - mean1) * rstd1 * gg.x + be.x, 0.f);
+      const float y3 = fmaxf((acc2[i][3] - mean1) * rstd1 * gg.y + be.y, 0.f);
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      *reinterpret_cast<uint32_t*>(sRoi + off512(r0, col >> 3) + (col & 7) * 2) = pack2h(y0, y1);
+      *reinterpret_cast<uint32_t*>(sRoi + off512(r1, col >> 3) + (col & 7) * 2) = pack2h(y2, y3);
+    }
+  }
+  __syncthreads();
+  {
+    __half* o = out + static_cast<long>(b) * NBIN * D;
+    for (int id = tid; id < NBIN * 32; id += 256) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sRoi + off512(id >> 5, id & 31));
+      *reinterpret_cast<uint4*>(o + id * 8) = v;
+    }
+  }
+}
+
+RoiLevels make_levels(const void* const* feats, const int* hs, const int* ws, const float* scales) {
+  RoiLevels lv;
+  for (int i = 0; i < 3; ++i) {
+    lv.feat[i] = static_cast<const __half*>(feats[i]);
+    lv.h[i] = hs[i];
+    lv.w[i] = ws[i];
+    lv.scale[i] = scales[i];
+  }
+  return lv;
+}
+
+}  // namespace
+
+int roi_align_launch(const void* const* feats, const int* hs, const int* ws, const float* scales, const float* boxes,
+                     int num_boxes, int boxes_per_frame, void* roi_out, float* mean_f32, void* mean_f16,
+                     cudaStream_t stream) {
+  if (num_boxes <= 0 || boxes_per_frame <= 0) return DVID_ERR_SHAPE;
+  roi_align_kernel<<<num_boxes, 256, 0, stream>>>(make_levels(feats, hs, ws, scales), boxes, boxes_per_frame,
+                                                  static_cast<__half*>(roi_out), mean_f32,
+                                                  static_cast<__half*>(mean_f16));
+  return check_launch();
+}
+
+int roi_dynconv_launch(const void* const* feats, const int* hs, const int* ws, const float* scales,
+                       const float* boxes, int num_boxes, int boxes_per_frame, const void* roi_in, const void* params,
+                       const float* g1, const float* b1, const float* g2, const float* b2, void* out,
+                       cudaStream_t stream) {
+  if (num_boxes <= 0 || boxes_per_frame <= 0) return DVID_ERR_SHAPE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(roi_dynconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(roi_dynconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) !=
+            cudaSuccess)
+      return DVID_ERR_CUDA;
+    attr_set = true;
+  }
+  const RoiLevels lv = make_levels(feats, hs, ws, scales);
+  if (roi_in != nullptr) {
+    roi_dynconv_kernel<true><<<num_boxes, 256, SM_TOTAL, stream>>>(
+        lv, boxes, boxes_per_frame, static_cast<const __half*>(roi_in), static_cast<const __half*>(params), g1, b1,
+        g2, b2, static_cast<__half*>(out));
+  } else {
+    roi_dynconv_kernel<false><<<num_boxes, 256, SM_TOTAL, stream>>>(
+        lv, boxes, boxes_per_frame, nullptr, static_cast<const __half*>(params), g1, b1, g2, b2,
+        static_cast<__half*>(out));
+  }
+  return check_launch();
+}
+
+}  // namespace dvid

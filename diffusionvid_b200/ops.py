@@ -1,0 +1,309 @@
+"""Torch-tensor front ends of the C ABI (include/dvid_b200.h).  PyTorch is used for device memory and streams only;
+every function launches hand-written sm_100a kernels from libdvid_b200.so on the current CUDA stream and raises
+DvidError when the library is missing or a call fails (no fallback)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, cur_stream, ptr
+
+LAUNCHES = 0   # number of kernel launches issued through this module (bench.py reports it as gpu_launches)
+
+
+def _cnt(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise _lib.DvidError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} "
+                             f"cuda={t.is_cuda} contiguous={t.is_contiguous()}")
+
+
+H = torch.float16
+F32 = torch.float32
+
+
+def require_device(dev):
+    """The product path is CUDA-only: raise unless `dev` is a CUDA device and the native library loads."""
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise _lib.DvidError("diffusionvid_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    _lib.lib()
+
+
+# ------------------------------------------------------------------------------------------------ dense
+def conv2d(x, w, bias, cout, R, S, stride, pad, relu, resid=None, resid_shift=0, out=None):
+    """x NHWC fp16, w [cout][R*S*cin] fp16 -> NHWC fp16."""
+    _chk(x, H, "x"); _chk(w, H, "w"); _chk(bias, F32, "bias"); _chk(resid, H, "resid")
+    n, h, wd, cin = x.shape
+    ho = (h + 2 * pad - R) // stride + 1
+    wo = (wd + 2 * pad - S) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), device=x.device, dtype=H)
+    check(_lib.lib().dvid_conv2d_nhwc_f16(ptr(x), ptr(w), ptr(bias), ptr(resid), ptr(out), n, h, wd, cin, cout, R, S,
+                                          stride, pad, resid_shift, int(relu), cur_stream()), "dvid_conv2d_nhwc_f16")
+    _cnt()
+    return out
+
+
+def stem_conv(x_haloed, w, bias, n, H_, W_, cout, relu=True, out=None):
+    _chk(x_haloed, H, "x"); _chk(w, H, "w"); _chk(bias, F32, "bias")
+    if out is None:
+        out = torch.empty((n, H_ // 2, W_ // 2, cout), device=x_haloed.device, dtype=H)
+    check(_lib.lib().dvid_stem_conv_f16(ptr(x_haloed), ptr(w), ptr(bias), ptr(out), n, H_, W_, cout, int(relu),
+                                        cur_stream()), "dvid_stem_conv_f16")
+    _cnt()
+    return out
+
+
+def gemm(a, w, bias=None, relu=False, resid=None, out=None):
+    """fp16 out: act(a @ w^T + bias + resid)."""
+    _chk(a, H, "a"); _chk(w, H, "w"); _chk(bias, F32, "bias"); _chk(resid, H, "resid")
+    m, k = a.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), device=a.device, dtype=H)
+    check(_lib.lib().dvid_gemm_f16(ptr(a), ptr(w), ptr(bias), ptr(resid), ptr(out), None, m, n, k, int(relu), 1, None,
+                                   cur_stream()), "dvid_gemm_f16")
+    _cnt()
+    return out
+
+
+def gemm_partials(a, w, splits=1, out=None):
+    """fp32 split-K partial sums [splits_used][m][n] (no bias); returns (partials, splits_used)."""
+    _chk(a, H, "a"); _chk(w, H, "w")
+    m, k = a.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((max(1, splits), m, n), device=a.device, dtype=F32)
+    used = ctypes.c_int(0)
+    check(_lib.lib().dvid_gemm_f16(ptr(a), ptr(w), None, None, None, ptr(out), m, n, k, 0, splits, ctypes.byref(used),
+                                   cur_stream()), "dvid_gemm_f16(partials)")
+    _cnt()
+    return out, used.value
+
+
+# ------------------------------------------------------------------------------------------------ image side
+def preprocess(img, mean, std, halo=3):
+    """img [n,3,H,W] fp32 in [0,1] -> [n, H+2*halo, W+2*halo, 8] fp16 normalised, zero halo."""
+    _chk(img, F32, "img")
+    n, _, h, w = img.shape
+    out = torch.empty((n, h + 2 * halo, w + 2 * halo, 8), device=img.device, dtype=H)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    check(_lib.lib().dvid_preprocess(ptr(img), ptr(out), n, h, w, halo, h + 2 * halo, w + 2 * halo, m, s,
+                                     cur_stream()), "dvid_preprocess")
+    _cnt()
+    return out
+
+
+def maxpool3x3s2(x):
+    _chk(x, H, "x")
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), device=x.device, dtype=H)
+    check(_lib.lib().dvid_maxpool3x3s2_nhwc_f16(ptr(x), ptr(out), n, h, w, c, cur_stream()), "dvid_maxpool")
+    _cnt()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ decoder
+def attention(q, k, v, out, batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs, q_bs, k_bs, v_bs, o_bs):
+    """q/k/v/out: fp16 tensors (possibly views into a packed buffer); strides in elements."""
+    for t, nme in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        if not t.is_cuda or t.dtype != H:
+            raise _lib.DvidError(f"attention: {nme} must be CUDA fp16")
+    check(_lib.lib().dvid_attention_hd32(ptr(q), ptr(k), ptr(v), ptr(out), batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs,
+                                         q_bs, k_bs, v_bs, o_bs, cur_stream()), "dvid_attention_hd32")
+    _cnt()
+    return out
+
+
+class Levels:
+    """The three FPN maps (NHWC fp16, [frames, h, w, 256]) as the host-side pointer arrays the C ABI takes."""
+
+    def __init__(self, feats, scales=(1 / 8., 1 / 16., 1 / 32.)):
+        for f in feats:
+            _chk(f, H, "feat")
+        self.feats = feats
+        self.ptrs = (ctypes.c_void_p * 3)(*[f.data_ptr() for f in feats])
+        self.hs = (ctypes.c_int * 3)(*[f.shape[1] for f in feats])
+        self.ws = (ctypes.c_int * 3)(*[f.shape[2] for f in feats])
+        self.scales = (ctypes.c_float * 3)(*scales)
+
+
+def roi_align(levels, boxes, boxes_per_frame, want_roi=True, want_mean=True):
+    _chk(boxes, F32, "boxes")
+    m = boxes.numel() // 4
+    dev = boxes.device
+    roi = torch.empty((m, 49, 256), device=dev, dtype=H) if want_roi else None
+    mean32 = torch.empty((m, 256), device=dev, dtype=F32) if want_mean else None
+    mean16 = torch.empty((m, 256), device=dev, dtype=H) if want_mean else None
+    check(_lib.lib().dvid_roi_align(levels.ptrs, levels.hs, levels.ws, levels.scales, ptr(boxes), m, boxes_per_frame,
+                                    ptr(roi), ptr(mean32), ptr(mean16), cur_stream()), "dvid_roi_align")
+    _cnt()
+    return roi, mean32, mean16
+
+
+def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=None, out=None):
+    _chk(boxes, F32, "boxes"); _chk(params, H, "params"); _chk(roi_in, H, "roi_in")
+    for t in (g1, b1, g2, b2):
+        _chk(t, F32, "ln")
+    m = params.shape[0]
+    if out is None:
+        out = torch.empty((m, 49 * 256), device=params.device, dtype=H)
+    lv = levels
+    check(_lib.lib().dvid_roi_dynconv(lv.ptrs if lv else None, lv.hs if lv else None, lv.ws if lv else None,
+                                      lv.scales if lv else None, ptr(boxes), m, boxes_per_frame, ptr(roi_in),
+                                      ptr(params), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(out), cur_stream()),
+          "dvid_roi_dynconv")
+    _cnt()
+    return out
+
+
+def row_post(M, partials=None, splits=1, in_f16=None, bias=None, ln1=None, relu1=False, resid=None, ln2=None, act2=0,
+             act2_f16_only=False, out_f32=None, out_f16=None, mod_scale=None, mod_shift=None, rows_per_group=1,
+             scale_stride=0, shift_stride=0, shift_per_row=False, out_mod_f16=None):
+    _chk(partials, F32, "partials"); _chk(in_f16, H, "in_f16"); _chk(bias, F32, "bias"); _chk(resid, F32, "resid")
+    _chk(out_f32, F32, "out_f32"); _chk(out_f16, H, "out_f16"); _chk(out_mod_f16, H, "out_mod_f16")
+    ln1g, ln1b = ln1 if ln1 is not None else (None, None)
+    ln2g, ln2b = ln2 if ln2 is not None else (None, None)
+    check(_lib.lib().dvid_row_post(ptr(partials), splits, M * 256, ptr(in_f16), ptr(bias), ptr(ln1g), ptr(ln1b),
+                                   int(relu1), ptr(resid), ptr(ln2g), ptr(ln2b), act2, int(act2_f16_only),
+                                   ptr(out_f32), ptr(out_f16), ptr(mod_scale), ptr(mod_shift), rows_per_group,
+                                   scale_stride, shift_stride, int(shift_per_row), ptr(out_mod_f16), M, cur_stream()),
+          "dvid_row_post")
+    _cnt()
+
+
+def small_linear(a, w, bias, act_in=0, act_out=0):
+    _chk(a, F32, "a"); _chk(w, H, "w"); _chk(bias, F32, "bias")
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty((m, n), device=a.device, dtype=F32)
+    check(_lib.lib().dvid_small_linear(ptr(a), ptr(w), ptr(bias), ptr(out), m, n, k, act_in, act_out, cur_stream()),
+          "dvid_small_linear")
+    _cnt()
+    return out
+
+
+def time_sinusoid(t, freq):
+    _chk(t, F32, "t"); _chk(freq, F32, "freq")
+    out = torch.empty((t.numel(), 256), device=t.device, dtype=F32)
+    check(_lib.lib().dvid_time_sinusoid(ptr(t), ptr(freq), ptr(out), t.numel(), cur_stream()), "dvid_time_sinusoid")
+    _cnt()
+    return out
+
+
+def head_final(logit_part, cls_bias, C, delta_part, delta_bias, boxes_in, logits_out=None, boxes_out=None):
+    _chk(logit_part, F32, "logit_part"); _chk(delta_part, F32, "delta_part"); _chk(boxes_in, F32, "boxes_in")
+    M = logit_part.shape[0]
+    dev = logit_part.device
+    if logits_out is None:
+        logits_out = torch.empty((M, C), device=dev, dtype=F32)
+    if boxes_out is None:
+        boxes_out = torch.empty((M, 4), device=dev, dtype=F32)
+    check(_lib.lib().dvid_head_final(ptr(logit_part), logit_part.shape[1], ptr(cls_bias), C, ptr(delta_part),
+                                     delta_part.shape[1], ptr(delta_bias), ptr(boxes_in), ptr(logits_out),
+                                     ptr(boxes_out), M, cur_stream()), "dvid_head_final")
+    _cnt()
+    return logits_out, boxes_out
+
+
+# ------------------------------------------------------------------------------------------------ diffusion loop
+def noise_to_boxes(x, scale, W, Hh):
+    _chk(x, F32, "x")
+    out = torch.empty_like(x)
+    check(_lib.lib().dvid_noise_to_boxes(ptr(x), ptr(out), x.numel() // 4, scale, W, Hh, cur_stream()),
+          "dvid_noise_to_boxes")
+    _cnt()
+    return out
+
+
+def ddim_step(logits, coord, x_t, eps, fill, scale, W, Hh, sqrt_recip_a, sqrt_recipm1_a, sqrt_a_next, c_coef, sigma):
+    for t in (logits, coord, x_t, eps, fill):
+        _chk(t, F32, "ddim input")
+    frames, N, C = logits.shape
+    x_next = torch.empty((frames, N, 4), device=logits.device, dtype=F32)
+    boxes_next = torch.empty((frames, N, 4), device=logits.device, dtype=F32)
+    kept = torch.empty((frames,), device=logits.device, dtype=torch.int32)
+    check(_lib.lib().dvid_ddim_step(ptr(logits), C, ptr(coord), ptr(x_t), ptr(eps), ptr(fill), ptr(x_next),
+                                    ptr(boxes_next), ptr(kept), frames, N, scale, W, Hh, sqrt_recip_a, sqrt_recipm1_a,
+                                    sqrt_a_next, c_coef, sigma, cur_stream()), "dvid_ddim_step")
+    _cnt()
+    return x_next, boxes_next, kept
+
+
+def topk_scores(logits, boxes, k, out_boxes, out_scores, out_labels, slot0):
+    _chk(logits, F32, "logits"); _chk(boxes, F32, "boxes")
+    frames, N, C = logits.shape
+    cap = out_scores.shape[1]
+    check(_lib.lib().dvid_topk_scores(ptr(logits), ptr(boxes), frames, N, C, k, ptr(out_boxes), ptr(out_scores),
+                                      ptr(out_labels), cap, slot0, cur_stream()), "dvid_topk_scores")
+    _cnt()
+
+
+def topk_mask(logits, k1, k2):
+    _chk(logits, F32, "logits")
+    frames, N, C = logits.shape
+    m1 = torch.empty((frames, N), device=logits.device, dtype=torch.uint8)
+    m2 = torch.empty((frames, N), device=logits.device, dtype=torch.uint8)
+    check(_lib.lib().dvid_topk_mask(ptr(logits), frames, N, C, k1, k2, ptr(m1), ptr(m2), cur_stream()),
+          "dvid_topk_mask")
+    _cnt()
+    return m1, m2
+
+
+def gather_masked_rows(src, mask, k):
+    _chk(src, F32, "src")
+    frames, N = mask.shape
+    dst = torch.empty((frames * k, 256), device=src.device, dtype=F32)
+    check(_lib.lib().dvid_gather_masked_rows(ptr(src), ptr(mask), frames, N, k, ptr(dst), cur_stream()),
+          "dvid_gather_masked_rows")
+    _cnt()
+    return dst
+
+
+def nms(boxes, scores, labels=None, counts=None, n=None, thr=0.5, plus_one=False, ge=False, ascending_out=False,
+        clip_wh=None, want_compact=True):
+    """boxes [frames][cap][4], scores [frames][cap], labels int32 [frames][cap] or None.
+    Returns dict(keep int64 [frames][cap], count int32 [frames], boxes/scores/labels compacted)."""
+    _chk(boxes, F32, "boxes"); _chk(scores, F32, "scores"); _chk(labels, torch.int32, "labels")
+    _chk(counts, torch.int32, "counts")
+    frames, cap = scores.shape
+    if n is None:
+        n = cap
+    dev = boxes.device
+    keep = torch.full((frames, cap), -1, device=dev, dtype=torch.int64)
+    count = torch.empty((frames,), device=dev, dtype=torch.int32)
+    ob = torch.empty((frames, cap, 4), device=dev, dtype=F32) if want_compact else None
+    os_ = torch.empty((frames, cap), device=dev, dtype=F32) if want_compact else None
+    ol = torch.empty((frames, cap), device=dev, dtype=torch.int32) if (want_compact and labels is not None) else None
+    cw, ch = clip_wh if clip_wh is not None else (0.0, 0.0)
+    check(_lib.lib().dvid_nms(ptr(boxes), ptr(scores), ptr(labels), ptr(counts), n, cap, frames, thr, int(plus_one),
+                              int(ge), int(ascending_out), cw, ch, ptr(keep), ptr(ob), ptr(os_), ptr(ol), ptr(count),
+                              cur_stream()), "dvid_nms")
+    _cnt()
+    return dict(keep=keep, count=count, boxes=ob, scores=os_, labels=ol)
+
+
+# ------------------------------------------------------------------------------------------------ global memory
+def cdist(x):
+    _chk(x, F32, "x")
+    n, d = x.shape
+    out = torch.empty((n, n), device=x.device, dtype=F32)
+    check(_lib.lib().dvid_cdist_f32(ptr(x), ptr(out), n, d, cur_stream()), "dvid_cdist_f32")
+    _cnt()
+    return out
+
+
+def furthest_point_sampling(b, n, m, dist, temp, idx):
+    """Same signature as mega_core._C.furthest_point_sampling (mega_core/csrc/fps.h:15-36); returns 1."""
+    _chk(dist, F32, "points"); _chk(temp, F32, "temp"); _chk(idx, torch.int32, "idx")
+    check(_lib.lib().dvid_furthest_point_sampling(b, n, m, ptr(dist), ptr(temp), ptr(idx), cur_stream()),
+          "dvid_furthest_point_sampling")
+    _cnt()
+    return 1

@@ -1,13 +1,16 @@
 /*
- * dvid_b200 — C ABI of the B200-native DiffusionVID inference hot path (libdvid_b200.so).
+ * dvid_b200 - C ABI of the B200-native DiffusionVID inference hot path (libdvid_b200.so).
  *
- * Every entry point takes plain device pointers, sizes and a CUDA stream (cudaStream_t passed as void*); no torch
- * types cross this boundary. All functions are asynchronous on `stream`, never synchronise, never allocate device
- * memory, and return 0 on success or a DVID_ERR_* code (they never exit the process — the reference's FPS launcher
- * calls exit(-1) on a launch error, mega_core/csrc/cuda/fps.cu:181-185).
+ * This library replaces, for the DiffusionDet/DiffusionVID model of sdroh1027/DiffusionVID, (a) the cuDNN/cuBLAS/ATen/
+ * torchvision kernels the reference reaches through PyTorch and detectron2 and (b) its native extension mega_core/_C
+ * (mega_core/csrc/vision.cpp:10-27).  Every entry point takes plain device pointers, sizes and a CUDA stream
+ * (cudaStream_t passed as void*); no torch types cross this boundary.  All functions are asynchronous on `stream`,
+ * never synchronise, never allocate device memory, and return 0 (DVID_OK) or a DVID_ERR_* code - they never exit the
+ * process (the reference's FPS launcher calls exit(-1) on a launch error, mega_core/csrc/cuda/fps.cu:181-185).
  *
- * Layout conventions: activations NHWC fp16 ("half"), weights [Cout][R*S*Cin] fp16, box coordinates / logits /
- * noise fp32, indices int32 unless stated. Citations are into /root/reference (sdroh1027/DiffusionVID @ 8375542).
+ * Layout conventions: activations NHWC fp16 ("half"), weights [Cout][R*S*Cin] fp16, box coordinates / logits / noise /
+ * object features fp32, indices int32 unless stated.  Citations are into /root/reference (DiffusionVID @ 8375542);
+ * "SURVEY A<n>" refers to the restated third-party semantics in SURVEY.md Appendix A.
  */
 #ifndef DVID_B200_H
 #define DVID_B200_H
@@ -36,7 +39,7 @@ DVID_API int dvid_abi_version(void);
 DVID_API int dvid_num_sms(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Dense contractions (tcgen05 + TMA).
+ * Dense contractions (tcgen05 + TMA + TMEM), csrc/conv_gemm.cu.
  *
  * dvid_conv2d_nhwc_f16 replaces the cuDNN convolutions behind detectron2's ResNet/FPN that the reference builds at
  * mega_core/modeling/detector/diffusion_det.py:219 and calls at :427 (FrozenBN folded into weight/bias by the host).
@@ -49,6 +52,12 @@ DVID_API int dvid_conv2d_nhwc_f16(const void* in, const void* weight, const floa
                          int n, int h, int w, int cin, int cout, int R, int S, int stride, int pad,
                          int resid_shift, int relu, void* stream);
 
+/* Stem: 7x7 / stride 2 / pad 3 convolution of the 3-channel image (detectron2 BasicStem) + ReLU.
+ * `in_haloed`: output of dvid_preprocess with halo 3: [n][H+6][W+6][8] fp16.  `weight`: [cout][7][8][8] fp16 with
+ * weight[co][r][s][c] = w[co][c][r][s] * bn_scale for s<7, c<3 and zero elsewhere.  out: [n][H/2][W/2][cout]. */
+DVID_API int dvid_stem_conv_f16(const void* in_haloed, const void* weight, const float* bias, void* out, int n, int H, int W,
+                       int cout, int relu, void* stream);
+
 /* dvid_gemm_f16 replaces torch.nn.functional.linear (cuBLAS) for every nn.Linear of the decoder
  * (mega_core/modeling/roi_heads/box_head/box_head.py:218-223,447-491,675-684):
  *   out_f16[m,n] = act( bias[n] + sum_k a[m,k] * w[n,k] + resid[m,n] )           (out_f32_partials == NULL)
@@ -58,6 +67,101 @@ DVID_API int dvid_conv2d_nhwc_f16(const void* in, const void* weight, const floa
 DVID_API int dvid_gemm_f16(const void* a, const void* w, const float* bias, const void* resid, void* out_f16,
                   float* out_f32_partials, int m, int n, int k, int relu, int splits, int* splits_used,
                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Image-side memory-bound kernels, csrc/rowops.cu.
+ */
+/* normalizer (diffusion_det.py:301-303, applied :422) + NCHW fp32 -> NHWC fp16 (8 channels, 3 real) with a zero halo.
+ * img [n][3][H][W] in [0,1]; out [n][Hp][Wp][8]; mean/std: 3 host floats (already divided by 255). */
+DVID_API int dvid_preprocess(const float* img, void* out, int n, int H, int W, int halo, int Hp, int Wp, const float* mean,
+                    const float* std, void* stream);
+/* max_pool2d(kernel 3, stride 2, pad 1) of the stem, NHWC fp16, C % 8 == 0. */
+DVID_API int dvid_maxpool3x3s2_nhwc_f16(const void* in, void* out, int n, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Decoder (DynamicHead) kernels.
+ */
+/* softmax(Q K^T / sqrt(32)) V for head dim 32 - the core of torch.nn.MultiheadAttention at box_head.py:516,626 (per
+ * frame self-attention) and :371 (global cross-attention).  fp16 in/out with element strides: row strides *_rs,
+ * batch strides *_bs; head h reads columns [32h, 32h+32) of each row. */
+DVID_API int dvid_attention_hd32(const void* q, const void* k, const void* v, void* o, int batch, int heads, int lq, int lk,
+                        long q_rs, long k_rs, long v_rs, long o_rs, long q_bs, long k_bs, long v_bs, long o_bs,
+                        void* stream);
+
+/* detectron2 ROIPooler -> torchvision roi_align(aligned=True, 7x7, sampling_ratio 2) over 3 FPN levels (call sites
+ * box_head.py:507,617).  feats: 3 host pointers to device NHWC fp16 maps [frames][h_l][w_l][256];
+ * boxes [num_boxes][4] xyxy fp32, box b belongs to frame b / boxes_per_frame.  roi_out [num_boxes][49][256] fp16
+ * (position-major, box_head.py:512) may be NULL; mean_* [num_boxes][256] = mean over the 49 positions
+ * (pro_features seed, box_head.py:509-510) may be NULL. */
+DVID_API int dvid_roi_align(const void* const* feats, const int* hs, const int* ws, const float* scales, const float* boxes,
+                   int num_boxes, int boxes_per_frame, void* roi_out, float* mean_f32, void* mean_f16, void* stream);
+
+/* Fused [ROIAlign +] DynamicConv bmm chain (box_head.py:698-704): out[b] = relu(LN256(relu(LN64(roi_b @ P1_b)) @ P2_b)),
+ * params [num_boxes][32768] fp16 = dynamic_layer output (P1 [256][64] then P2 [64][256], box_head.py:693-696).
+ * roi_in == NULL: the ROI tile is gathered in-kernel from feats/boxes (fused ROIAlign); else read from roi_in.
+ * out [num_boxes][49][256] fp16 (input of out_layer). */
+DVID_API int dvid_roi_dynconv(const void* const* feats, const int* hs, const int* ws, const float* scales, const float* boxes,
+                     int num_boxes, int boxes_per_frame, const void* roi_in, const void* params, const float* ln1_g,
+                     const float* ln1_b, const float* ln2_g, const float* ln2_b, void* out, void* stream);
+
+/* Row kernel for 256-wide rows: y = sum_s partials[s] (or in_f16) + bias -> [LN1] -> [ReLU] -> [+resid] -> [LN2] ->
+ * act2 (0 none / 1 ReLU / 2 SiLU; on the fp16 output only if act2_f16_only) -> out_f32 / out_f16; optional time /
+ * condition modulation out_mod_f16 = y * (scale[row / rows_per_group] + 1) + shift (box_head.py:533-536, :643-647).
+ * Implements every LayerNorm / residual / activation between the decoder GEMMs (box_head.py:517-529,540-543,707-709). */
+DVID_API int dvid_row_post(const float* partials, int splits, long split_stride, const void* in_f16, const float* bias,
+                  const float* ln1_g, const float* ln1_b, int relu1, const float* resid, const float* ln2_g,
+                  const float* ln2_b, int act2, int act2_f16_only, float* out_f32, void* out_f16,
+                  const float* mod_scale, const float* mod_shift, int rows_per_group, int scale_stride,
+                  int shift_stride, int shift_per_row, void* out_mod_f16, int M, void* stream);
+
+/* out[m][n] = act_out(bias[n] + sum_k act_in(a[m][k]) * w[n][k]) for m <= 8 rows: time_mlp (box_head.py:218-223) and
+ * block_time_mlp (:464,:602).  a fp32, w fp16 [n][k], act_in 1 = SiLU, act_out 1 = GELU(erf). */
+DVID_API int dvid_small_linear(const float* a, const void* w, const float* bias, float* out, int m, int n, int k, int act_in,
+                      int act_out, void* stream);
+/* SinusoidalPositionEmbeddings (box_head.py:729-741), dim 256: out[m][256] = [sin(t*freq), cos(t*freq)]. */
+DVID_API int dvid_time_sinusoid(const float* t, const float* freq, float* out, int m, void* stream);
+
+/* class_logits / bboxes_delta bias + RCNNHead.apply_deltas (box_head.py:544-590). */
+DVID_API int dvid_head_final(const float* logit_part, int ldl, const float* cls_bias, int C, const float* delta_part, int ldd,
+                    const float* delta_bias, const float* boxes_in, float* logits_out, float* boxes_out, int M,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Diffusion loop, csrc/rowops.cu + csrc/postproc.cu.
+ */
+/* DiffusionDet.model_predictions input map (diffusion_det.py:657-660): noise-space cxcywh -> absolute xyxy. */
+DVID_API int dvid_noise_to_boxes(const float* x, float* boxes, int M, float scale, float W, float H, void* stream);
+/* One DDIM step with box renewal, one CTA per frame (diffusion_det.py:559-596 and :668-676).  Scalars are the fp32
+ * schedule constants the host derives in float64 exactly as the reference does (:578-584). */
+DVID_API int dvid_ddim_step(const float* logits, int C, const float* coord, const float* x_t, const float* eps,
+                   const float* fill, float* x_next, float* boxes_next, int* num_kept, int frames, int N, float scale,
+                   float W, float H, float sqrt_recip_a, float sqrt_recipm1_a, float sqrt_a_next, float c_coef,
+                   float sigma, void* stream);
+/* DiffusionDet.inference per-frame top-k of the N*C sigmoid scores (diffusion_det.py:772-784); results are written at
+ * slot0 of per-frame candidate buffers of capacity `cap` (the ensemble concatenation of :608-610). */
+DVID_API int dvid_topk_scores(const float* logits, const float* boxes, int frames, int N, int C, int k, float* out_boxes,
+                     float* out_scores, int* out_labels, int cap, int slot0, void* stream);
+/* Per-frame top-k1 / top-k2 masks of the max logit (box_head.py:304-311) and the masked row gather (:315-317). */
+DVID_API int dvid_topk_mask(const float* logits, int frames, int N, int C, int k1, int k2, unsigned char* mask1,
+                   unsigned char* mask2, void* stream);
+DVID_API int dvid_gather_masked_rows(const float* src, const unsigned char* mask, int frames, int N, int k, float* dst,
+                            void* stream);
+/* Greedy NMS, one CTA per frame, n <= 1024 candidates, sweep on the device.  labels != NULL: torchvision batched_nms
+ * coordinate trick (diffusion_det.py:617,793).  plus_one/ge/ascending_out select the legacy mega_core._C.nms
+ * semantics (mega_core/csrc/cpu/nms_cpu.cpp:5-65, cuda/nms.cu:13-67).  clip_w>0 applies BoxList.clip_to_image
+ * (mega_core/structures/bounding_box.py:214-224) to out_boxes.  keep_idx is int64 like the reference's return. */
+DVID_API int dvid_nms(const float* boxes, const float* scores, const int* labels, const int* counts, int n, int cap,
+             int frames, float thr, int plus_one, int ge, int ascending_out, float clip_w, float clip_h,
+             long long* keep_idx, float* out_boxes, float* out_scores, int* out_labels, int* out_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Global memory management (diffusion_det.py:841-896).
+ */
+/* torch.cdist(x, x, p=2) by direct differences, fp32 (diffusion_det.py:880). */
+DVID_API int dvid_cdist_f32(const float* x, float* out, int n, int d, void* stream);
+/* Drop-in for mega_core._C.furthest_point_sampling (mega_core/csrc/fps.h:15-36, cuda/fps.cu:25-185): dist (b,n,n) fp32,
+ * temp (b,n) pre-filled with 1e10, idx (b,m) int32; identical picks including the kernel's tie-breaking. */
+DVID_API int dvid_furthest_point_sampling(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,10 +32,11 @@ def roi_align(feat, rois, out_size, scale, sampling_ratio):
     y2 = rois[:, 4] * scale - 0.5
     bin_w = (x2 - x1) / P
     bin_h = (y2 - y1) / P
-    grid = (torch.arange(P * S, dtype=feat.dtype) // S).to(feat.dtype) + \
-           ((torch.arange(P * S) % S).to(feat.dtype) + 0.5) / S          # ph + (iy + .5)/S, length P*S
-    ys = y1[:, None] + grid[None, :] * bin_h[:, None]                     # (K, P*S)
-    xs = x1[:, None] + grid[None, :] * bin_w[:, None]
+    pbin = (torch.arange(P * S) // S).to(feat.dtype)[None, :]              # ph for each of the P*S sample rows
+    frac = ((torch.arange(P * S) % S).to(feat.dtype) + 0.5)[None, :]       # iy + .5
+    # torchvision: y = roi_start_h + ph * bin_size_h + (iy + .5f) * bin_size_h / roi_bin_grid_h  (same op order)
+    ys = y1[:, None] + pbin * bin_h[:, None] + frac * bin_h[:, None] / S   # (K, P*S)
+    xs = x1[:, None] + pbin * bin_w[:, None] + frac * bin_w[:, None] / S
 
     def prep(v, size):
         invalid = (v < -1.0) | (v > size)

