@@ -196,7 +196,7 @@ class DiffusionDet(nn.Module):
         return pk
 
     # ------------------------------------------------------------------------------------------ backbone
-    def backbone(self, imgs):
+    def extract_features(self, imgs):
         """imgs [n,3,Hp,Wp] fp32 in [0,1] on the device -> [p3,p4,p5] NHWC fp16 (detectron2 R-101 + FPN)."""
         pk = self._pk or self._pack()
         n, _, Hh, Ww = imgs.shape
@@ -398,12 +398,13 @@ class DiffusionDet(nn.Module):
 
         # 1. features + base stages for the new local / global frames
         if ref_l or ref_g:
-            total = torch.cat([i.tensors for i in ref_l + ref_g]).to(dev, F32)
+            # host images are copied one by one (asynchronously when pinned) and concatenated on the device
+            total = torch.cat([i.tensors.to(dev, F32, non_blocking=True) for i in ref_l + ref_g])
             len_l = len(ref_l)
             lg_all, bx_all, o32_all, o16_all, k1_all, k2_all, f_all = [], [], [], [], [], [], []
             for bi, split in enumerate(total.split(ib)):
                 B = split.shape[0]
-                f = self.backbone(split)
+                f = self.extract_features(split)
                 lv = ops.Levels(f)
                 box_init = self._randn("init", fid, bi, B, dev)
                 boxes = ops.noise_to_boxes(box_init, scale, float(w), float(h))

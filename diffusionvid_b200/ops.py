@@ -9,11 +9,36 @@ from . import _lib
 from ._lib import check, cur_stream, ptr
 
 LAUNCHES = 0   # number of kernel launches issued through this module (bench.py reports it as gpu_launches)
+PROFILE = None  # when a dict: family -> [list of (start_event, end_event), flops, bytes]; filled by _prof (bench.py)
 
 
 def _cnt(n=1):
     global LAUNCHES
     LAUNCHES += n
+
+
+class _prof:
+    """Context manager: when ops.PROFILE is a dict, bracket one launch with CUDA events on the launching stream and
+    account its algorithmic FLOPs / bytes under `family` (bench.py's live per-kernel roofline measurement)."""
+
+    def __init__(self, family, flops=0.0, nbytes=0.0):
+        self.family, self.flops, self.nbytes = family, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e.record()
+            rec = PROFILE.setdefault(self.family, [[], 0.0, 0.0])
+            rec[0].append((self.s, self.e))
+            rec[1] += self.flops
+            rec[2] += self.nbytes
+        return False
 
 
 def _chk(t, dtype, name):
@@ -44,8 +69,11 @@ def conv2d(x, w, bias, cout, R, S, stride, pad, relu, resid=None, resid_shift=0,
     wo = (wd + 2 * pad - S) // stride + 1
     if out is None:
         out = torch.empty((n, ho, wo, cout), device=x.device, dtype=H)
-    check(_lib.lib().dvid_conv2d_nhwc_f16(ptr(x), ptr(w), ptr(bias), ptr(resid), ptr(out), n, h, wd, cin, cout, R, S,
-                                          stride, pad, resid_shift, int(relu), cur_stream()), "dvid_conv2d_nhwc_f16")
+    with _prof("conv_gemm", 2.0 * n * ho * wo * cout * R * S * cin,
+               2.0 * (x.numel() + w.numel() + n * ho * wo * cout * (2 if resid is not None else 1))):
+        check(_lib.lib().dvid_conv2d_nhwc_f16(ptr(x), ptr(w), ptr(bias), ptr(resid), ptr(out), n, h, wd, cin, cout, R,
+                                              S, stride, pad, resid_shift, int(relu), cur_stream()),
+              "dvid_conv2d_nhwc_f16")
     _cnt()
     return out
 
@@ -54,8 +82,9 @@ def stem_conv(x_haloed, w, bias, n, H_, W_, cout, relu=True, out=None):
     _chk(x_haloed, H, "x"); _chk(w, H, "w"); _chk(bias, F32, "bias")
     if out is None:
         out = torch.empty((n, H_ // 2, W_ // 2, cout), device=x_haloed.device, dtype=H)
-    check(_lib.lib().dvid_stem_conv_f16(ptr(x_haloed), ptr(w), ptr(bias), ptr(out), n, H_, W_, cout, int(relu),
-                                        cur_stream()), "dvid_stem_conv_f16")
+    with _prof("conv_gemm", 2.0 * n * (H_ // 2) * (W_ // 2) * cout * 147, 2.0 * (x_haloed.numel() + out.numel())):
+        check(_lib.lib().dvid_stem_conv_f16(ptr(x_haloed), ptr(w), ptr(bias), ptr(out), n, H_, W_, cout, int(relu),
+                                            cur_stream()), "dvid_stem_conv_f16")
     _cnt()
     return out
 
@@ -67,8 +96,9 @@ def gemm(a, w, bias=None, relu=False, resid=None, out=None):
     n = w.shape[0]
     if out is None:
         out = torch.empty((m, n), device=a.device, dtype=H)
-    check(_lib.lib().dvid_gemm_f16(ptr(a), ptr(w), ptr(bias), ptr(resid), ptr(out), None, m, n, k, int(relu), 1, None,
-                                   cur_stream()), "dvid_gemm_f16")
+    with _prof("conv_gemm", 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n)):
+        check(_lib.lib().dvid_gemm_f16(ptr(a), ptr(w), ptr(bias), ptr(resid), ptr(out), None, m, n, k, int(relu), 1,
+                                       None, cur_stream()), "dvid_gemm_f16")
     _cnt()
     return out
 
@@ -81,8 +111,9 @@ def gemm_partials(a, w, splits=1, out=None):
     if out is None:
         out = torch.empty((max(1, splits), m, n), device=a.device, dtype=F32)
     used = ctypes.c_int(0)
-    check(_lib.lib().dvid_gemm_f16(ptr(a), ptr(w), None, None, None, ptr(out), m, n, k, 0, splits, ctypes.byref(used),
-                                   cur_stream()), "dvid_gemm_f16(partials)")
+    with _prof("conv_gemm", 2.0 * m * n * k, 2.0 * (m * k + n * k) + 4.0 * m * n * max(1, splits)):
+        check(_lib.lib().dvid_gemm_f16(ptr(a), ptr(w), None, None, None, ptr(out), m, n, k, 0, splits,
+                                       ctypes.byref(used), cur_stream()), "dvid_gemm_f16(partials)")
     _cnt()
     return out, used.value
 
@@ -116,8 +147,9 @@ def attention(q, k, v, out, batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs, q_bs, 
     for t, nme in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         if not t.is_cuda or t.dtype != H:
             raise _lib.DvidError(f"attention: {nme} must be CUDA fp16")
-    check(_lib.lib().dvid_attention_hd32(ptr(q), ptr(k), ptr(v), ptr(out), batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs,
-                                         q_bs, k_bs, v_bs, o_bs, cur_stream()), "dvid_attention_hd32")
+    with _prof("attention", 4.0 * batch * heads * lq * lk * 32, 2.0 * batch * heads * 32 * (2 * lq + 2 * lk)):
+        check(_lib.lib().dvid_attention_hd32(ptr(q), ptr(k), ptr(v), ptr(out), batch, heads, lq, lk, q_rs, k_rs, v_rs,
+                                             o_rs, q_bs, k_bs, v_bs, o_bs, cur_stream()), "dvid_attention_hd32")
     _cnt()
     return out
 
@@ -142,8 +174,10 @@ def roi_align(levels, boxes, boxes_per_frame, want_roi=True, want_mean=True):
     roi = torch.empty((m, 49, 256), device=dev, dtype=H) if want_roi else None
     mean32 = torch.empty((m, 256), device=dev, dtype=F32) if want_mean else None
     mean16 = torch.empty((m, 256), device=dev, dtype=H) if want_mean else None
-    check(_lib.lib().dvid_roi_align(levels.ptrs, levels.hs, levels.ws, levels.scales, ptr(boxes), m, boxes_per_frame,
-                                    ptr(roi), ptr(mean32), ptr(mean16), cur_stream()), "dvid_roi_align")
+    with _prof("roi_align", 2.0 * m * 49 * 16 * 256, 2.0 * m * 49 * 256 * (16 + 1)):
+        check(_lib.lib().dvid_roi_align(levels.ptrs, levels.hs, levels.ws, levels.scales, ptr(boxes), m,
+                                        boxes_per_frame, ptr(roi), ptr(mean32), ptr(mean16), cur_stream()),
+              "dvid_roi_align")
     _cnt()
     return roi, mean32, mean16
 
@@ -156,10 +190,12 @@ def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=N
     if out is None:
         out = torch.empty((m, 49 * 256), device=params.device, dtype=H)
     lv = levels
-    check(_lib.lib().dvid_roi_dynconv(lv.ptrs if lv else None, lv.hs if lv else None, lv.ws if lv else None,
-                                      lv.scales if lv else None, ptr(boxes), m, boxes_per_frame, ptr(roi_in),
-                                      ptr(params), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(out), cur_stream()),
-          "dvid_roi_dynconv")
+    # algorithmic: two 49x256x64 bmm per box; bytes: generated weights in, 49x256 activations out (+ROI tile in)
+    with _prof("roi_dynconv", 4.0 * m * 49 * 256 * 64, 2.0 * m * (32768 + 49 * 256 * 2)):
+        check(_lib.lib().dvid_roi_dynconv(lv.ptrs if lv else None, lv.hs if lv else None, lv.ws if lv else None,
+                                          lv.scales if lv else None, ptr(boxes), m, boxes_per_frame, ptr(roi_in),
+                                          ptr(params), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(out), cur_stream()),
+              "dvid_roi_dynconv")
     _cnt()
     return out
 
