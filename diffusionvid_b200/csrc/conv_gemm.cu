@@ -46,7 +46,8 @@ struct ConvGemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int SMEM_BYTES =
-      STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+      STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+      BN * 4 /*bias staging*/;
 };
 
 template <int BN>
@@ -65,6 +66,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sBias = reinterpret_cast<float*>(sOut + 2 * OUT_STAGE_BYTES + 256);   // [BN] bias of the current tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,12 +162,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // Global-memory latency is kept off the per-chunk critical path: the bias of the NEXT tile is fetched into
+    // registers while the current tile is processed (and staged through smem), the residual of chunk c+1 is fetched
+    // while chunk c is converted.
     const int ew = warp - 4;  // == warp % 4: the TMEM sub-partition this warp may read
     const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 128;
     const bool store_leader = (threadIdx.x == 128);
     int staged = 0;
     int as = 0;
     uint32_t aphase = 0;
+    float bnext[BN / 128 > 0 ? BN / 128 : 1];
+    auto fetch_bias = [&](int tile) {
+      const int n0 = (tile % p.n_tiles) * BN;
+#pragma unroll
+      for (int i = 0; i < (BN + 127) / 128; ++i) {
+        const int col = n0 + et + i * 128;
+        bnext[i] = (p.bias != nullptr && (BN >= 128 || et < BN) && col < p.cout) ? __ldg(p.bias + col) : 0.f;
+      }
+    };
+    if (blockIdx.x < total_tiles && p.out_f32 == nullptr) fetch_bias(blockIdx.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_idx = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
@@ -178,6 +194,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int x = x0 + (row & (tw - 1));
       const int y = y0 + (row >> p.tw_log2);
       const bool valid = (x < p.w_out) && (y < p.h_out);
+      const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
+
+      const __half* rrow = nullptr;   // this thread's residual row (channel 0)
+      if (p.resid != nullptr && valid) {
+        rrow = p.resid + ((static_cast<long long>(img) * p.resid_h + (y >> p.resid_shift)) * p.resid_w +
+                          (x >> p.resid_shift)) * p.cout;
+      }
+      uint4 rnext[8];
+      auto fetch_resid = [&](int c) {
+        const int ch0 = n_idx * BN + c * 64;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          rnext[q] = (rrow != nullptr && ch0 + q * 8 < p.cout)
+                         ? __ldg(reinterpret_cast<const uint4*>(rrow + ch0 + q * 8))
+                         : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (p.resid != nullptr) fetch_resid(0);
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -205,44 +239,47 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
-        long long resid_off = 0;
-        if (p.resid != nullptr && valid) {
-          resid_off = ((static_cast<long long>(img) * p.resid_h + (y >> p.resid_shift)) * p.resid_w +
-                       (x >> p.resid_shift)) * p.cout;
-        }
+        // stage this tile's bias (all epilogue threads passed the last barrier of the previous tile, so nobody still
+        // reads the old values), then start fetching the next tile's.
+#pragma unroll
+        for (int i = 0; i < (BN + 127) / 128; ++i)
+          if (BN >= 128 || et < BN) sBias[et + i * 128] = bnext[i];
+        if (tile + static_cast<int>(gridDim.x) < total_tiles) fetch_bias(tile + gridDim.x);
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = 0; c < nchunks; ++c) {
           const int ch0 = n_idx * BN + c * 64;
-          if (ch0 >= p.cout) break;
           uint8_t* buf = sOut + (staged & 1) * OUT_STAGE_BYTES;
+          uint4 rcur[8];
+          if (p.resid != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
+            if (c + 1 < nchunks) fetch_resid(c + 1);
+          }
           if (store_leader) tma_store_wait_read<1>();  // the store that last read this buffer has drained it
-          named_bar_sync(1, 128);
+          named_bar_sync(1, 128);                      // also publishes sBias
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t v[32];
             tmem_ld32(tbase + c * 64 + h * 32, v);
             tmem_ld_wait();
-            const int chh = ch0 + h * 32;
             float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (chh + j < p.cout) f[j] += __ldg(p.bias + chh + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sBias + c * 64 + h * 32 + j);
+              f[j] = __uint_as_float(v[j]) + b4.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
             }
-            if (p.resid != nullptr && valid) {
+            if (p.resid != nullptr) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                if (chh + q * 8 < p.cout) {
-                  const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.resid + resid_off + chh + q * 8));
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rcur[h * 4 + q]);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 rf = __half22float2(rh[e]);
-                    f[q * 8 + 2 * e] += rf.x;
-                    f[q * 8 + 2 * e + 1] += rf.y;
-                  }
+                for (int e = 0; e < 4; ++e) {
+                  const float2 rf = __half22float2(rh[e]);
+                  f[q * 8 + 2 * e] += rf.x;
+                  f[q * 8 + 2 * e + 1] += rf.y;
                 }
               }
             }
