@@ -260,11 +260,16 @@ def run_ours(args):
 
         roof = None
         if rank == 0 and not args.no_roofline:
+            # per-launch CUDA events need eager, single-stream execution (the timed runs above replay CUDA graphs)
+            ug, us = m.use_graphs, m.use_streams
+            m.use_graphs = m.use_streams = False
+            run_clip(m, dev_samples, False)
             ops.PROFILE = {}
             run_clip(m, dev_samples, False)
             torch.cuda.synchronize()
             prof = ops.PROFILE
             ops.PROFILE = None
+            m.use_graphs, m.use_streams = ug, us
             fam = {}
             for k, (evs, flops, nbytes) in prof.items():
                 t = sum(s.elapsed_time(e) for s, e in evs)

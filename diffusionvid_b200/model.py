@@ -94,15 +94,24 @@ class DiffusionDet(nn.Module):
         self.register_buffer("posterior_mean_coef2", (1. - acp) * torch.sqrt(alphas) / (1. - ac))
         self._pk = None
         self._sched = None
+        # execution policy (CUDA only): captured graphs per unit, frames of a batch spread over parallel streams
+        self.use_graphs = bool(hp.get("use_graphs", True))
+        self.use_streams = bool(hp.get("use_streams", True))
+        self.frames_per_stream = int(hp.get("frames_per_stream", 4))
+        self.debug_trace = False
+        self._graphs = {}
+        self._streams = []
         self.eval()
 
     # ------------------------------------------------------------------------------------------ weight packing
     def _apply(self, fn, *a, **kw):   # .to()/.cuda()/.half() invalidate the packed copies
         self._pk = None
+        self._graphs = {}
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):
         self._pk = None
+        self._graphs = {}
         return super().load_state_dict(*a, **kw)
 
     def _pack(self):
@@ -313,12 +322,12 @@ class DiffusionDet(nn.Module):
             logits, boxes, pro32, pro16 = self._head(e, lv, boxes, pro32, pro16, t)
         return logits, boxes, pro32, pro16
 
-    def _cond_shift(self, e, obj16, M):
+    def _cond_shift(self, e, obj16, M, kv=None):
         """global cross-attention (box_head.py:366-371) -> SiLU -> c_mlp (box_head.py:644): per-row shift (M,256)."""
         ga = self._pk["ga"]
         dev = obj16.device
         q = ops.gemm(obj16, ga["q_w"], ga["q_b"])
-        kv = self._mem_kv
+        kv = self._mem_kv if kv is None else kv
         ctx = torch.empty((M, 256), device=dev, dtype=H)
         ops.attention(q, kv, kv[:, 256:], ctx, 1, 8, M, kv.shape[0], 256, 512, 512, 256, 0, 0, 0, 0)
         part, s = ops.gemm_partials(ctx, ga["o_w"], 1)
@@ -359,6 +368,150 @@ class DiffusionDet(nn.Module):
             return self.noise.get(kind, self._video, key_frame, index, frames).to(dev, non_blocking=True).contiguous()
         return torch.randn((frames, N, 4), device=dev, dtype=F32)
 
+    # ------------------------------------------------------------------------------------------ execution units
+    def _fork_join(self, fns):
+        """Run the independent callables `fns` concurrently, one CUDA stream each (frames never interact inside the
+        backbone or the decoder: self-attention is per frame, box_head.py:515-516), and join on the current stream.
+        Inside a graph capture this records parallel branches; on CPU (test shim) it runs them in order."""
+        if len(fns) == 1 or torch.device(self.device).type != "cuda" or not self.use_streams:
+            return [f() for f in fns]
+        cur = torch.cuda.current_stream()
+        while len(self._streams) < len(fns):
+            self._streams.append(torch.cuda.Stream())
+        outs = []
+        for f, st in zip(fns, self._streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(f())
+        for st in self._streams[:len(fns)]:
+            cur.wait_stream(st)
+        return outs
+
+    def _groups(self, B):
+        g = max(1, int(self.frames_per_stream))
+        if not self.use_streams or torch.device(self.device).type != "cuda":
+            g = B
+        return [(i, min(B, i + g)) for i in range(0, B, g)]
+
+    def _extract(self, imgs, box_init, w, h):
+        """Backbone + head_series[0..num_heads) at t=999 + top-k memory candidates for B new frames
+        (diffusion_det.py:418-460; box_head.py:286-317).  All outputs are per frame."""
+        hp = self.hp
+        N = self.num_proposals
+        k1, k2 = min(hp["topk"][0], N), min(hp["topk"][1], N)
+
+        def unit(i0, i1):
+            def run():
+                f = self.extract_features(imgs[i0:i1])
+                lv = ops.Levels(f)
+                boxes = ops.noise_to_boxes(box_init[i0:i1].contiguous(), hp["snr_scale"], float(w), float(h))
+                lg, bx, o32, o16 = self._base_stages(lv, boxes, 999)
+                m1, m2 = ops.topk_mask(lg, k1, k2)
+                B = i1 - i0
+                return (f, lg, bx, o32.view(B, N, 256), o16.view(B, N, 256),
+                        ops.gather_masked_rows(o32, m1, k1).view(B, k1, 256),
+                        ops.gather_masked_rows(o32, m2, k2).view(B, k2, 256))
+            return run
+
+        outs = self._fork_join([unit(i0, i1) for i0, i1 in self._groups(imgs.shape[0])])
+        if len(outs) == 1:
+            f, lg, bx, o32, o16, c1, c2 = outs[0]
+            return dict(p3=f[0], p4=f[1], p5=f[2], lg=lg, bx=bx, o32=o32, o16=o16, k1=c1, k2=c2)
+        cat = lambda i: torch.cat([o[i] for o in outs])
+        return dict(p3=torch.cat([o[0][0] for o in outs]), p4=torch.cat([o[0][1] for o in outs]),
+                    p5=torch.cat([o[0][2] for o in outs]), lg=cat(1), bx=cat(2), o32=cat(3), o16=cat(4), k1=cat(5),
+                    k2=cat(6))
+
+    def _ddim_consts(self, t, t_next):
+        """float64 scalar math of diffusion_det.py:578-584, rounded to fp32 like the reference's tensors."""
+        a = self._ac[t].to(torch.float64); an = self._ac[t_next].to(torch.float64)
+        sig2 = (1 - a / an) * (1 - an) / (1 - a)
+        sigma = float(sig2.sqrt().to(F32)); cc = float((1 - an - sig2).sqrt().to(F32))
+        sra = float(torch.sqrt(1. / self._ac[t])); srm1 = float(torch.sqrt(1. / self._ac[t] - 1))
+        san = float(self._ac[t_next].sqrt())
+        return sra, srm1, san, cc, sigma
+
+    def _decode(self, p3, p4, p5, img, eps, fill, w, h, mem_kv=None, c_lg=None, c_bx=None, c_o32=None, c_o16=None,
+                trace=None, fid=0):
+        """The DDIM sampling loop + ensemble + NMS for one key batch (diffusion_det.py:526-633).
+        img (B,N,4); eps/fill (T-1,B,N,4) step noise; c_*: cached stage outputs (T == 1, box_head.py:300-302)."""
+        hp = self.hp
+        pk = self._pk
+        N = self.num_proposals
+        T = hp["sample_step"]
+        scale = hp["snr_scale"]
+        times = list(reversed(torch.linspace(-1, 999, steps=T + 1).int().tolist()))
+        pairs = list(zip(times[:-1], times[1:]))
+        cap = max(1, T - 1) * N
+        use_cond = hp["global_enable"] and hp["num_heads_local"] > 0
+
+        def unit(i0, i1):
+            def run():
+                B = i1 - i0
+                M = B * N
+                dev = img.device
+                lv = ops.Levels([p3[i0:i1], p4[i0:i1], p5[i0:i1]])
+                x = img[i0:i1].contiguous()
+                boxes = ops.noise_to_boxes(x, scale, float(w), float(h))
+                ens_b = torch.empty((B, cap, 4), device=dev, dtype=F32)
+                ens_s = torch.empty((B, cap), device=dev, dtype=F32)
+                ens_l = torch.empty((B, cap), device=dev, dtype=torch.int32)
+                logits = coord = None
+                for si, (t, t_next) in enumerate(pairs):
+                    if T > 1:
+                        lg, bx, o32, o16 = self._base_stages(lv, boxes, t)
+                    else:   # sampling_timesteps == 1: reuse the cached stage outputs (box_head.py:300-302)
+                        lg, bx = c_lg[i0:i1], c_bx[i0:i1]
+                        o32, o16 = c_o32[i0:i1].reshape(M, 256), c_o16[i0:i1].reshape(M, 256)
+                    if use_cond:
+                        for e in pk["cond"]:
+                            shift = self._cond_shift(e, o16.contiguous(), M, mem_kv)
+                            lg, bx, o32, o16 = self._head(e, lv, bx.contiguous(), o32.contiguous(), o16.contiguous(),
+                                                          t, shift_rows=shift)
+                    logits, coord = lg.contiguous(), bx.contiguous()
+                    if trace is not None:
+                        trace[("logits", fid, si, i0)] = logits
+                        trace[("coord", fid, si, i0)] = coord
+                    if t_next < 0:
+                        break
+                    sra, srm1, san, cc, sigma = self._ddim_consts(t, t_next)
+                    x, boxes, _ = ops.ddim_step(logits, coord, x, eps[si, i0:i1].contiguous(),
+                                                fill[si, i0:i1].contiguous(), scale, float(w), float(h), sra, srm1,
+                                                san, cc, sigma)
+                    if trace is not None:
+                        trace[("img", fid, si, i0)] = x
+                    if T > 1:
+                        ops.topk_scores(logits, coord, N, ens_b, ens_s, ens_l, si * N)
+                if T == 1:
+                    ops.topk_scores(logits, coord, N, ens_b, ens_s, ens_l, 0)
+                if hp["use_nms"]:
+                    r = ops.nms(ens_b, ens_s, ens_l, thr=0.5, clip_wh=(float(w), float(h)))
+                    return r["count"], r["boxes"], r["scores"], r["labels"]
+                cnt = torch.full((B,), cap, device=dev, dtype=torch.int32)
+                ob = torch.stack([ens_b[..., 0].clamp(0, w - 1), ens_b[..., 1].clamp(0, h - 1),
+                                  ens_b[..., 2].clamp(0, w - 1), ens_b[..., 3].clamp(0, h - 1)], dim=-1)
+                return cnt, ob, ens_s, ens_l
+            return run
+
+        outs = self._fork_join([unit(i0, i1) for i0, i1 in self._groups(img.shape[0])])
+        if len(outs) == 1:
+            cnt, ob, osc, ol = outs[0]
+        else:
+            cnt, ob, osc, ol = (torch.cat([o[i] for o in outs]) for i in range(4))
+        return dict(count=cnt, boxes=ob, scores=osc, labels=ol)
+
+    def _run_unit(self, name, fn, key, tensors, consts):
+        """Execute `fn(**tensors, **consts)`; on CUDA through a captured graph keyed by (name, key, shapes)."""
+        dev = torch.device(self.device)
+        if dev.type != "cuda" or not self.use_graphs:
+            return fn(**tensors, **consts)
+        sig = (name, key) + tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(tensors.items()) if v is not None)
+        g = self._graphs.get(sig)
+        if g is None:
+            g = _CapturedUnit(fn, tensors, consts)
+            self._graphs[sig] = g
+        return g(tensors)
+
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, images, targets=None):
         if self.training:
@@ -373,9 +526,14 @@ class DiffusionDet(nn.Module):
         ref_g = [to_image_list(i) for i in images["ref_g"]]
         return self._forward_test(cur, ref_l, ref_g, images)
 
+    def _warm_constants(self, times):
+        """time_mlp / block_time_mlp outputs depend only on the timestep: fill the caches outside any capture."""
+        for t in times:
+            for e in self._pk["heads"] + self._pk["cond"]:
+                self._mod(e, t)
+
     def _forward_test(self, imgs, ref_l, ref_g, infos):
         hp = self.hp
-        pk = self._pk
         dev = torch.device(self.device)
         N = self.num_proposals
         ib = self.infer_batch
@@ -394,32 +552,27 @@ class DiffusionDet(nn.Module):
         self.local_img_queue = []
         h, w = imgs.image_sizes[0]
         h, w = int(h), int(w)
-        scale = hp["snr_scale"]
+        T = hp["sample_step"]
+        times = list(reversed(torch.linspace(-1, 999, steps=T + 1).int().tolist()))
+        self._warm_constants([999] + times[:-1])
 
         # 1. features + base stages for the new local / global frames
         if ref_l or ref_g:
             # host images are copied one by one (asynchronously when pinned) and concatenated on the device
             total = torch.cat([i.tensors.to(dev, F32, non_blocking=True) for i in ref_l + ref_g])
             len_l = len(ref_l)
-            lg_all, bx_all, o32_all, o16_all, k1_all, k2_all, f_all = [], [], [], [], [], [], []
+            outs = []
             for bi, split in enumerate(total.split(ib)):
                 B = split.shape[0]
-                f = self.extract_features(split)
-                lv = ops.Levels(f)
                 box_init = self._randn("init", fid, bi, B, dev)
-                boxes = ops.noise_to_boxes(box_init, scale, float(w), float(h))
-                lg, bx, o32, o16 = self._base_stages(lv, boxes, 999)
-                k1, k2 = min(hp["topk"][0], N), min(hp["topk"][1], N)
-                m1, m2 = ops.topk_mask(lg, k1, k2)
-                k1_all.append(ops.gather_masked_rows(o32, m1, k1).view(B, k1, 256))
-                k2_all.append(ops.gather_masked_rows(o32, m2, k2).view(B, k2, 256))
-                lg_all.append(lg); bx_all.append(bx); o32_all.append(o32.view(B, N, 256))
-                o16_all.append(o16.view(B, N, 256)); f_all.append(f)
-            lg_t = torch.cat(lg_all); bx_t = torch.cat(bx_all); o32_t = torch.cat(o32_all); o16_t = torch.cat(o16_all)
-            feats_t = [torch.cat([f[l] for f in f_all]) if len(f_all) > 1 else f_all[0][l] for l in range(3)]
+                o = self._run_unit("extract", self._extract, (w, h), dict(imgs=split.contiguous(), box_init=box_init),
+                                   dict(w=w, h=h))
+                # unit outputs live in graph-owned buffers that the next replay overwrites: keep private copies
+                outs.append({k: v.clone() for k, v in o.items()} if self._graph_active() else o)
+            ex = {k: (torch.cat([o[k] for o in outs]) if len(outs) > 1 else outs[0][k]) for k in outs[0]}
             if ref_g and hp["global_enable"]:
-                g1 = torch.cat(k1_all)[len_l:].reshape(-1, 256)
-                g2 = torch.cat(k2_all)[len_l:].reshape(-1, 256)
+                g1 = ex["k1"][len_l:].reshape(-1, 256)
+                g2 = ex["k2"][len_l:].reshape(-1, 256)
                 self._set_memory([self._update_memory(g1, self.proposal_feats_global[0], hp["mem_size"]),
                                   self._update_memory(g2, self.proposal_feats_global[1], hp["mem_size2"])])
             if infos["frame_category"] == 0:
@@ -430,67 +583,34 @@ class DiffusionDet(nn.Module):
             else:
                 fill = list(range(len_l))
             for i in fill:
-                self.feats.append([feats_t[l][i:i + 1] for l in range(3)])
-                self.cache.append((lg_t[i:i + 1], bx_t[i:i + 1], o32_t[i], o16_t[i]))
+                self.feats.append([ex[l][i:i + 1] for l in ("p3", "p4", "p5")])
+                self.cache.append((ex["lg"][i:i + 1], ex["bx"][i:i + 1], ex["o32"][i:i + 1], ex["o16"][i:i + 1]))
 
         # 2. the key batch
         batch = min(ib, infos["end_id"] - fid + 1)
         r0 = hp["key_frame_location"]
         idxs = range(r0, r0 + batch)
-        feats_cur = [torch.cat([self.feats[i][l] for i in idxs]) for l in range(3)]
-        lv = ops.Levels(feats_cur)
-        T = hp["sample_step"]
-        times = list(reversed(torch.linspace(-1, 999, steps=T + 1).int().tolist()))
-        pairs = list(zip(times[:-1], times[1:]))
-        img = self._randn("img", fid, 0, batch, dev)
-        boxes = ops.noise_to_boxes(img, scale, float(w), float(h))
-        M = batch * N
-        cap = max(1, T - 1) * N
-        ens_b = torch.empty((batch, cap, 4), device=dev, dtype=F32)
-        ens_s = torch.empty((batch, cap), device=dev, dtype=F32)
-        ens_l = torch.empty((batch, cap), device=dev, dtype=torch.int32)
-        use_cond = hp["global_enable"] and hp["num_heads_local"] > 0
-        logits = coord = None
-        self.last_trace = {}
-        for si, (t, t_next) in enumerate(pairs):
-            if T > 1:
-                lg, bx, o32, o16 = self._base_stages(lv, boxes, t)
-            else:   # sampling_timesteps == 1: reuse the cached stage outputs (box_head.py:300-302)
-                lg = torch.cat([self.cache[i][0] for i in idxs]); bx = torch.cat([self.cache[i][1] for i in idxs])
-                o32 = torch.cat([self.cache[i][2] for i in idxs]); o16 = torch.cat([self.cache[i][3] for i in idxs])
-            if use_cond:
-                for e in pk["cond"]:
-                    shift = self._cond_shift(e, o16, M)
-                    lg, bx, o32, o16 = self._head(e, lv, bx.contiguous(), o32.contiguous(), o16.contiguous(), t,
-                                                  shift_rows=shift)
-            logits, coord = lg.contiguous(), bx.contiguous()
-            self.last_trace[("logits", fid, si)] = logits
-            self.last_trace[("coord", fid, si)] = coord
-            if t_next < 0:
-                break
-            a = self._ac[t].to(torch.float64); an = self._ac[t_next].to(torch.float64)
-            sig2 = (1 - a / an) * (1 - an) / (1 - a)
-            sigma = float(sig2.sqrt().to(F32)); cc = float((1 - an - sig2).sqrt().to(F32))
-            sra = float(torch.sqrt(1. / self._ac[t])); srm1 = float(torch.sqrt(1. / self._ac[t] - 1))
-            san = float(self._ac[t_next].sqrt())
-            eps = self._randn("eps", fid, si, batch, dev)
-            fillz = self._randn("fill", fid, si, batch, dev)
-            img, boxes, _ = ops.ddim_step(logits, coord, img, eps, fillz, scale, float(w), float(h), sra, srm1, san, cc,
-                                          sigma)
-            self.last_trace[("img", fid, si)] = img
-            if T > 1:
-                ops.topk_scores(logits, coord, N, ens_b, ens_s, ens_l, si * N)
-        if T == 1:
-            ops.topk_scores(logits, coord, N, ens_b, ens_s, ens_l, 0)
-        if hp["use_nms"]:
-            r = ops.nms(ens_b, ens_s, ens_l, thr=0.5, clip_wh=(float(w), float(h)))
-            counts = r["count"].cpu().tolist()       # the one device->host read of the batch
-            ob, osc, ol = r["boxes"], r["scores"], r["labels"]
+        tensors = dict(p3=torch.cat([self.feats[i][0] for i in idxs]), p4=torch.cat([self.feats[i][1] for i in idxs]),
+                       p5=torch.cat([self.feats[i][2] for i in idxs]), img=self._randn("img", fid, 0, batch, dev))
+        if T > 1:
+            tensors["eps"] = torch.stack([self._randn("eps", fid, si, batch, dev) for si in range(T - 1)])
+            tensors["fill"] = torch.stack([self._randn("fill", fid, si, batch, dev) for si in range(T - 1)])
         else:
-            counts = [cap] * batch
-            ob = torch.stack([ens_b[..., 0].clamp(0, w - 1), ens_b[..., 1].clamp(0, h - 1),
-                              ens_b[..., 2].clamp(0, w - 1), ens_b[..., 3].clamp(0, h - 1)], dim=-1)
-            osc, ol = ens_s, ens_l
+            tensors["eps"] = tensors["fill"] = None
+            for j, nm in enumerate(("c_lg", "c_bx", "c_o32", "c_o16")):
+                tensors[nm] = torch.cat([self.cache[i][j] for i in idxs])
+        if hp["global_enable"] and hp["num_heads_local"] > 0:
+            tensors["mem_kv"] = self._mem_kv
+        consts = dict(w=w, h=h)
+        if self.debug_trace:
+            self.last_trace = {}
+            r = self._decode(**tensors, **consts, trace=self.last_trace, fid=fid)
+        else:
+            r = self._run_unit("decode", self._decode, (w, h), tensors, consts)
+        counts = r["count"].cpu().tolist()       # the one device->host read of the batch
+        ob, osc, ol = r["boxes"], r["scores"], r["labels"]
+        if self._graph_active():
+            ob, osc, ol = ob.clone(), osc.clone(), ol.clone()
         results = []
         for i in range(batch):
             c = counts[i]
@@ -499,3 +619,35 @@ class DiffusionDet(nn.Module):
             bl.add_field("labels", ol[i, :c].long())
             results.append(bl)
         return results
+
+    def _graph_active(self):
+        return self.use_graphs and torch.device(self.device).type == "cuda"
+
+
+class _CapturedUnit:
+    """One execution unit captured into a CUDA graph: static input buffers, graph-owned outputs.  Replays cost one
+    launch on the host instead of ~10^3 (the reference's loop issues >10^3 ATen kernels per batch with >= 10 host
+    syncs); parallel per-frame branches inside the unit become parallel graph branches."""
+
+    def __init__(self, fn, tensors, consts):
+        self.static = {k: (v.clone() if v is not None else None) for k, v in tensors.items()}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):       # warm-up: lazy inits (function attributes, caches) happen outside capture
+            fn(**self.static, **consts)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.LAUNCHES
+        with torch.cuda.graph(self.graph):
+            self.out = fn(**self.static, **consts)
+        self.launches = ops.LAUNCHES - l0
+
+    def __call__(self, tensors):
+        for k, v in tensors.items():
+            if v is not None:
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        ops.LAUNCHES += self.launches
+        return self.out

@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--width", type=int, default=1000)
     ap.add_argument("--warm", type=int, default=1)
     ap.add_argument("--blocks", default="3,4,23,3")
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-streams", action="store_true")
+    ap.add_argument("--frames-per-stream", type=int, default=2)
     a = ap.parse_args()
     from diffusionvid_b200 import model as pm, synth
     dev = torch.device("cuda", 0)
@@ -35,9 +38,12 @@ def main():
     m = pm.DiffusionDet(hp)
     m.load_state_dict(synth.make_state_dict(seed=1234, blocks=blocks), strict=False)
     m.to(dev)
+    m.use_graphs = not a.no_graphs
+    m.use_streams = not a.no_streams
+    m.frames_per_stream = a.frames_per_stream
     samples, _ = bench.make_clip_inputs(a, dev, pinned=False)
     with torch.no_grad():
-        for _ in range(a.warm):
+        for _ in range(a.warm + (0 if a.no_graphs else 1)):
             bench.run_clip(m, samples, False)
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
