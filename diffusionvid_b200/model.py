@@ -101,6 +101,7 @@ class DiffusionDet(nn.Module):
         self.debug_trace = False
         self._graphs = {}
         self._streams = []
+        self._shard = None
         self.eval()
 
     # ------------------------------------------------------------------------------------------ weight packing
@@ -556,23 +557,41 @@ class DiffusionDet(nn.Module):
         times = list(reversed(torch.linspace(-1, 999, steps=T + 1).int().tolist()))
         self._warm_constants([999] + times[:-1])
 
+        rank, world = self._shard[:2] if self._shard is not None else (0, 1)
+
         # 1. features + base stages for the new local / global frames
         if ref_l or ref_g:
-            # host images are copied one by one (asynchronously when pinned) and concatenated on the device
-            total = torch.cat([i.tensors.to(dev, F32, non_blocking=True) for i in ref_l + ref_g])
-            len_l = len(ref_l)
-            outs = []
-            for bi, split in enumerate(total.split(ib)):
-                B = split.shape[0]
-                box_init = self._randn("init", fid, bi, B, dev)
-                o = self._run_unit("extract", self._extract, (w, h), dict(imgs=split.contiguous(), box_init=box_init),
-                                   dict(w=w, h=h))
-                # unit outputs live in graph-owned buffers that the next replay overwrites: keep private copies
-                outs.append({k: v.clone() for k, v in o.items()} if self._graph_active() else o)
-            ex = {k: (torch.cat([o[k] for o in outs]) if len(outs) > 1 else outs[0][k]) for k in outs[0]}
+            all_imgs = ref_l + ref_g
+            n_total, len_l = len(all_imgs), len(ref_l)
+            # frame sharding (SURVEY.md 8e mode B): frame i of this call belongs to rank i % world
+            mine = [i for i in range(n_total) if i % world == rank]
+            pos = {g: j for j, g in enumerate(mine)}
+            ex = None
+            if mine:
+                # host images are copied one by one (asynchronously when pinned) and concatenated on the device
+                total = torch.cat([all_imgs[i].tensors.to(dev, F32, non_blocking=True) for i in mine])
+                if world == 1:
+                    inits = [self._randn("init", fid, bi, min(ib, n_total - bi * ib), dev)
+                             for bi in range((n_total + ib - 1) // ib)]
+                    box_all = torch.cat(inits) if len(inits) > 1 else inits[0]
+                else:   # the reference draws one (B,N,4) tensor per split of `ib` frames: row = frame % ib
+                    cache = {}
+                    rows = []
+                    for i in mine:
+                        bi = i // ib
+                        if bi not in cache:
+                            cache[bi] = self._randn("init", fid, bi, min(ib, n_total - bi * ib), dev)
+                        rows.append(cache[bi][i % ib:i % ib + 1])
+                    box_all = torch.cat(rows)
+                outs = []
+                for split, binit in zip(total.split(ib), box_all.split(ib)):
+                    o = self._run_unit("extract", self._extract, (w, h),
+                                       dict(imgs=split.contiguous(), box_init=binit.contiguous()), dict(w=w, h=h))
+                    # unit outputs live in graph-owned buffers that the next replay overwrites: keep private copies
+                    outs.append({k: v.clone() for k, v in o.items()} if self._graph_active() else o)
+                ex = {k: (torch.cat([o[k] for o in outs]) if len(outs) > 1 else outs[0][k]) for k in outs[0]}
             if ref_g and hp["global_enable"]:
-                g1 = ex["k1"][len_l:].reshape(-1, 256)
-                g2 = ex["k2"][len_l:].reshape(-1, 256)
+                g1, g2 = self._gather_global_candidates(ex, pos, len_l, n_total, dev)
                 self._set_memory([self._update_memory(g1, self.proposal_feats_global[0], hp["mem_size"]),
                                   self._update_memory(g2, self.proposal_feats_global[1], hp["mem_size2"])])
             if infos["frame_category"] == 0:
@@ -583,42 +602,110 @@ class DiffusionDet(nn.Module):
             else:
                 fill = list(range(len_l))
             for i in fill:
-                self.feats.append([ex[l][i:i + 1] for l in ("p3", "p4", "p5")])
-                self.cache.append((ex["lg"][i:i + 1], ex["bx"][i:i + 1], ex["o32"][i:i + 1], ex["o16"][i:i + 1]))
+                if i in pos:
+                    j = pos[i]
+                    self.feats.append([ex[l][j:j + 1] for l in ("p3", "p4", "p5")])
+                    self.cache.append((ex["lg"][j:j + 1], ex["bx"][j:j + 1], ex["o32"][j:j + 1], ex["o16"][j:j + 1]))
+                else:       # another rank owns this frame
+                    self.feats.append(None)
+                    self.cache.append(None)
 
-        # 2. the key batch
+        # 2. the key batch (this rank's frames of it)
         batch = min(ib, infos["end_id"] - fid + 1)
         r0 = hp["key_frame_location"]
         idxs = range(r0, r0 + batch)
-        tensors = dict(p3=torch.cat([self.feats[i][0] for i in idxs]), p4=torch.cat([self.feats[i][1] for i in idxs]),
-                       p5=torch.cat([self.feats[i][2] for i in idxs]), img=self._randn("img", fid, 0, batch, dev))
-        if T > 1:
-            tensors["eps"] = torch.stack([self._randn("eps", fid, si, batch, dev) for si in range(T - 1)])
-            tensors["fill"] = torch.stack([self._randn("fill", fid, si, batch, dev) for si in range(T - 1)])
-        else:
-            tensors["eps"] = tensors["fill"] = None
-            for j, nm in enumerate(("c_lg", "c_bx", "c_o32", "c_o16")):
-                tensors[nm] = torch.cat([self.cache[i][j] for i in idxs])
-        if hp["global_enable"] and hp["num_heads_local"] > 0:
-            tensors["mem_kv"] = self._mem_kv
-        consts = dict(w=w, h=h)
-        if self.debug_trace:
-            self.last_trace = {}
-            r = self._decode(**tensors, **consts, trace=self.last_trace, fid=fid)
-        else:
-            r = self._run_unit("decode", self._decode, (w, h), tensors, consts)
+        own = [k for k, i in enumerate(idxs) if self.feats[i] is not None]
+        cap = max(1, T - 1) * N
+        r = None
+        if own:
+            sel = [idxs[k] for k in own]
+            pick = (lambda t: t) if len(own) == batch else (lambda t: t[own].contiguous())
+            tensors = dict(p3=torch.cat([self.feats[i][0] for i in sel]), p4=torch.cat([self.feats[i][1] for i in sel]),
+                           p5=torch.cat([self.feats[i][2] for i in sel]),
+                           img=pick(self._randn("img", fid, 0, batch, dev)))
+            if T > 1:
+                tensors["eps"] = torch.stack([pick(self._randn("eps", fid, si, batch, dev)) for si in range(T - 1)])
+                tensors["fill"] = torch.stack([pick(self._randn("fill", fid, si, batch, dev)) for si in range(T - 1)])
+            else:
+                tensors["eps"] = tensors["fill"] = None
+                for j, nm in enumerate(("c_lg", "c_bx", "c_o32", "c_o16")):
+                    tensors[nm] = torch.cat([self.cache[i][j] for i in sel])
+            if hp["global_enable"] and hp["num_heads_local"] > 0:
+                tensors["mem_kv"] = self._mem_kv
+            consts = dict(w=w, h=h)
+            if self.debug_trace:
+                self.last_trace = {}
+                r = self._decode(**tensors, **consts, trace=self.last_trace, fid=fid)
+            else:
+                r = self._run_unit("decode", self._decode, (w, h), tensors, consts)
+        if world > 1:
+            r = self._exchange_results(r, own, batch, cap, dev)
         counts = r["count"].cpu().tolist()       # the one device->host read of the batch
         ob, osc, ol = r["boxes"], r["scores"], r["labels"]
-        if self._graph_active():
+        if self._graph_active() and world == 1:
             ob, osc, ol = ob.clone(), osc.clone(), ol.clone()
         results = []
         for i in range(batch):
-            c = counts[i]
+            c = int(counts[i])
             bl = BoxList(ob[i, :c], (w, h), mode="xyxy")
             bl.add_field("scores", osc[i, :c])
             bl.add_field("labels", ol[i, :c].long())
             results.append(bl)
         return results
+
+    # ------------------------------------------------------------------------------------------ frame sharding
+    def set_frame_sharding(self, rank, world, group=None):
+        """SURVEY.md 8e mode B: the frames of every clip are dealt round-robin to the `world` ranks of `group`
+        (torch.distributed; NCCL on GPUs).  Every rank must be fed the same sample stream; per video one all-gather
+        moves the top-75/top-25 memory candidates of the global frames, per key batch one all-reduce assembles the
+        detections, so every rank returns the full result list.  world == 1 disables sharding."""
+        self._shard = (int(rank), int(world), group) if world > 1 else None
+
+    def _gather_global_candidates(self, ex, pos, len_l, n_total, dev):
+        """(G*75,256) / (G*25,256) memory candidates of the global frames in frame order (diffusion_det.py:476-488)."""
+        hp = self.hp
+        N = self.num_proposals
+        k1, k2 = min(hp["topk"][0], N), min(hp["topk"][1], N)
+        if self._shard is None:
+            return ex["k1"][len_l:].reshape(-1, 256), ex["k2"][len_l:].reshape(-1, 256)
+        import torch.distributed as dist
+        rank, world, group = self._shard
+        gl = list(range(len_l, n_total))
+        per = max(1, max(sum(1 for i in gl if i % world == r) for r in range(world)))
+        send = torch.zeros((per, k1 + k2, 256), device=dev, dtype=F32)
+        for j, i in enumerate([i for i in gl if i % world == rank]):
+            send[j, :k1] = ex["k1"][pos[i]]
+            send[j, k1:] = ex["k2"][pos[i]]
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send, group=group)
+        seen = [0] * world
+        rows = []
+        for i in gl:
+            r = i % world
+            rows.append(recv[r][seen[r]])
+            seen[r] += 1
+        allc = torch.stack(rows)
+        return allc[:, :k1].reshape(-1, 256).contiguous(), allc[:, k1:].reshape(-1, 256).contiguous()
+
+    def _exchange_results(self, r, own, batch, cap, dev):
+        """Each rank fills the rows of its own frames in a zero [batch, 1 + 6*cap] fp32 tensor (count | boxes | scores |
+        labels; counts <= cap and labels <= 30 are exact in fp32) and one SUM all-reduce replicates the batch."""
+        import torch.distributed as dist
+        _, _, group = self._shard
+        buf = torch.zeros((batch, 1 + 6 * cap), device=dev, dtype=F32)
+        if own:
+            idx = torch.tensor(own, device=dev, dtype=torch.long)
+            n = len(own)
+            c = r["count"].to(F32).view(n, 1)
+            valid = torch.arange(cap, device=dev)[None, :] < r["count"].view(n, 1)     # rows past count are undefined
+            zero = torch.zeros((), device=dev, dtype=F32)
+            row = torch.cat([c, torch.where(valid[..., None], r["boxes"], zero).reshape(n, -1),
+                             torch.where(valid, r["scores"], zero), torch.where(valid, r["labels"].to(F32), zero)],
+                            dim=1)
+            buf[idx] = row
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        return dict(count=buf[:, 0].round().to(torch.int32), boxes=buf[:, 1:1 + 4 * cap].reshape(batch, cap, 4),
+                    scores=buf[:, 1 + 4 * cap:1 + 5 * cap], labels=buf[:, 1 + 5 * cap:].round().to(torch.int32))
 
     def _graph_active(self):
         return self.use_graphs and torch.device(self.device).type == "cuda"
