@@ -67,6 +67,44 @@ def backbone_state_dict(g, blocks=R101_BLOCKS, fpn_ch=256):
     return sd
 
 
+def swin_state_dict(g, embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32), ws=7, fpn_ch=256):
+    """Swin backbone + FPN keys of build_swintransformer_fpn_backbone (mega_core/modeling/backbone/swintransformer.py:
+    464-751): trunc-normal(.02)-like Linear weights, small biases, LayerNorm near identity; FPN on swin1..3."""
+    sd = {}
+    p = "backbone.bottom_up."
+    sd[p + "patch_embed.proj.weight"] = torch.randn(embed, 3, 4, 4, generator=g) * math.sqrt(1.0 / 48)
+    sd[p + "patch_embed.proj.bias"] = 0.02 * torch.randn(embed, generator=g)
+    _ln(sd, g, p + "patch_embed.norm", embed)
+    for i, (d, nh) in enumerate(zip(depths, heads)):
+        C = embed * 2 ** i
+        for b in range(d):
+            pre = "%slayers.%d.blocks.%d." % (p, i, b)
+            _ln(sd, g, pre + "norm1", C)
+            sd[pre + "attn.qkv.weight"] = torch.randn(3 * C, C, generator=g) * math.sqrt(1.0 / C)
+            sd[pre + "attn.qkv.bias"] = 0.02 * torch.randn(3 * C, generator=g)
+            sd[pre + "attn.proj.weight"] = torch.randn(C, C, generator=g) * (0.5 * math.sqrt(1.0 / C))
+            sd[pre + "attn.proj.bias"] = 0.02 * torch.randn(C, generator=g)
+            sd[pre + "attn.relative_position_bias_table"] = 0.5 * torch.randn((2 * ws - 1) ** 2, nh, generator=g)
+            _ln(sd, g, pre + "norm2", C)
+            sd[pre + "mlp.fc1.weight"] = torch.randn(4 * C, C, generator=g) * math.sqrt(1.0 / C)
+            sd[pre + "mlp.fc1.bias"] = 0.02 * torch.randn(4 * C, generator=g)
+            sd[pre + "mlp.fc2.weight"] = torch.randn(C, 4 * C, generator=g) * (0.5 * math.sqrt(1.0 / (4 * C)))
+            sd[pre + "mlp.fc2.bias"] = 0.02 * torch.randn(C, generator=g)
+        if i < len(depths) - 1:
+            pre = "%slayers.%d.downsample." % (p, i)
+            _ln(sd, g, pre + "norm", 4 * C)
+            sd[pre + "reduction.weight"] = torch.randn(2 * C, 4 * C, generator=g) * math.sqrt(1.0 / (4 * C))
+        if i >= 1:
+            _ln(sd, g, "%snorm%d" % (p, i), C)
+    for lvl, i in ((3, 1), (4, 2), (5, 3)):
+        c = embed * 2 ** i
+        for kind, k, ci in (("lateral", 1, c), ("output", 3, fpn_ch)):
+            name = "backbone.fpn_%s%d" % (kind, lvl)
+            sd[name + ".weight"] = _xavier(g, fpn_ch, ci, k, k)
+            sd[name + ".bias"] = 0.02 * torch.randn(fpn_ch, generator=g)
+    return sd
+
+
 def _rcnn_head(sd, g, pre, d, dd, ff, ncls, num_cls, num_reg, cond, cls_bias, pool=7):
     sd[pre + "self_attn.in_proj_weight"] = _xavier(g, 3 * d, d)
     sd[pre + "self_attn.in_proj_bias"] = 0.02 * torch.randn(3 * d, generator=g)
@@ -112,9 +150,10 @@ def head_state_dict(g, num_heads=3, num_heads_local=1, d=256, dd=64, ff=2048, nc
     return sd
 
 
-def make_state_dict(seed=1234, blocks=R101_BLOCKS, **head_kw):
+def make_state_dict(seed=1234, blocks=R101_BLOCKS, swin=None, **head_kw):
+    """swin: None for the R-x+FPN backbone, else dict(embed=, depths=, heads=) for Swin + FPN."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    sd = backbone_state_dict(g, blocks)
+    sd = swin_state_dict(g, **swin) if swin else backbone_state_dict(g, blocks)
     sd.update(head_state_dict(g, **head_kw))
     return sd
 

@@ -111,3 +111,19 @@ def test_clip_matches_reference_forward_test(gold, setup, T):
     assert min(fracs) >= 0.98 and sum(fracs) / len(fracs) >= 0.995, fracs
     same = sum(int(g_["scores"].numel() == r["scores"].numel()) for g_, r in zip(got, ref))
     assert same >= L - 1
+
+
+def test_swin_body_matches_reference_swintransformer():
+    """oracle.swin.swin_body vs the reference's own swintransformer.py (tests/golden/make_golden_swin.py): patch embed,
+    W-MSA / SW-MSA with zero-padded windows (24x40 tokens -> 28x42), relative position bias, shift mask, patch merging
+    with odd sizes (3x5 at the last stage), per-output LayerNorm."""
+    from oracle import swin
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_swin_small.pt"), weights_only=False)
+    m = gold["meta"]
+    sd = synth.make_state_dict(seed=m["weight_seed"], swin=m["cfg"])
+    x = torch.randn(*m["shape"], generator=torch.Generator().manual_seed(m["input_seed"]))
+    out = swin.swin_body(om.Ctx(sd, om.Quant(False)), x)
+    assert set(out) == set(gold["out"])
+    for k, ref in gold["out"].items():
+        assert out[k].shape == ref.shape
+        assert (out[k] - ref).abs().max().item() <= 2e-4, k
