@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--backbone", default="r101", choices=["r101", "swinb"],
+                    help="r101: vid_R_101_DiffusionVID.yaml (headline); swinb: vid_Swin_B_DiffusionVID.yaml "
+                         "(INFER_BATCH 4, ALL_FRAME_INTERVAL 4)")
     ap.add_argument("--shard", default="videos", choices=["videos", "frames"],
                     help="N>1: 'videos' = every rank runs its own clips (reference scheme, weak scaling); 'frames' = "
                          "the frames of ONE clip are dealt to the ranks, one all-gather of memory candidates per "
@@ -180,10 +183,11 @@ def make_clip_inputs(args, dev, pinned):
     size = [(args.height, args.width)]
     samples = []
     for f in range(L):
+        mo = 3 if getattr(args, "backbone", "r101") == "swinb" else 7      # MODEL.VID.MEGA.MAX_OFFSET
         if f == 0:
-            ref_l = list(range(0, min(7, L - 1) + 1)); ref_g = gidx
+            ref_l = list(range(0, min(mo, L - 1) + 1)); ref_g = gidx
         else:
-            ref_l = [min(f + 7, L - 1)]; ref_g = []
+            ref_l = [min(f + mo, L - 1)]; ref_g = []
         samples.append(dict(cur=structures.ImageList(store[f:f + 1], size),
                             ref_l=[structures.ImageList(store[i:i + 1], size) for i in ref_l],
                             ref_g=[structures.ImageList(store[i:i + 1], size) for i in ref_g],
@@ -247,8 +251,11 @@ def run_ours(args):
     from diffusionvid_b200 import model as pm, ops, synth
 
     hp = dict(HP_BASE, num_proposals=args.proposals, sample_step=args.T, device=str(dev))
+    if args.backbone == "swinb":
+        hp.update(swin=dict(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32)), infer_batch=4,
+                  all_frame_interval=4)
     m = pm.DiffusionDet(hp)
-    m.load_state_dict(synth.make_state_dict(seed=1234, blocks=hp["blocks"]), strict=False)
+    m.load_state_dict(synth.make_state_dict(seed=1234, blocks=hp["blocks"], swin=hp.get("swin")), strict=False)
     m.to(dev)
     shard_frames = dist and args.shard == "frames"
     if shard_frames:
@@ -308,9 +315,11 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if shard_frames else "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "vid_R_101_DiffusionVID.yaml N=%d T=%d fp16, R-101+FPN, %dx%d clip of %d frames + %d "
-                                   "global frames per step, %s across ranks"
-                                   % (args.proposals, args.T, args.width, args.height, args.frames, args.global_frames,
+            "config": {"workload": "%s N=%d T=%d fp16, %dx%d clip of %d frames + %d global frames per step, %s "
+                                   "across ranks"
+                                   % ("vid_Swin_B_DiffusionVID.yaml Swin-B+FPN" if args.backbone == "swinb"
+                                      else "vid_R_101_DiffusionVID.yaml R-101+FPN",
+                                      args.proposals, args.T, args.width, args.height, args.frames, args.global_frames,
                                       "frame-sharded" if shard_frames else "video-sharded"),
                        "frames_per_step": args.frames, "l2": "inputs larger than L2 (clip %.0f MB fp32, feature maps "
                                                              "52 MB per key batch)" % (args.frames * 7.47)},

@@ -42,6 +42,10 @@ SIGNATURES = {
     "dvid_nms": [P, P, P, P, I, I, I, F, I, I, I, F, F, P, P, P, P, P, P],
     "dvid_cdist_f32": [P, P, I, I, P],
     "dvid_furthest_point_sampling": [I, I, I, P, P, P, P],
+    "dvid_swin_rows": [P, I, P, I, P, P, P, P, I, I, I, I, I, I, P],
+    "dvid_swin_patch_merge": [P, I, I, I, I, P, P, P, P],
+    "dvid_swin_patch_gather": [P, P, I, I, I, P, P, P],
+    "dvid_swin_window_attention": [P, P, P, I, I, I, I, I, I, P],
 }
 
 

@@ -135,6 +135,16 @@ def _get(node, path, default=None):
     return cur
 
 
+# size2config of mega_core/modeling/backbone/swintransformer.py:660-717 (window 7 variants)
+SWIN_SIZES = {
+    "T": dict(embed=96, depths=(2, 2, 6, 2), heads=(3, 6, 12, 24)),
+    "S": dict(embed=96, depths=(2, 2, 18, 2), heads=(3, 6, 12, 24)),
+    "B": dict(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32)),
+    "B-22k": dict(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32)),
+    "L-22k": dict(embed=192, depths=(2, 2, 18, 2), heads=(6, 12, 24, 48)),
+}
+
+
 def hot_path_params(cfg):
     """Flatten a CfgNode (ours or yacs) - or pass through a plain dict - into the model's parameter dict."""
     if isinstance(cfg, dict) and not isinstance(cfg, CfgNode) and "num_proposals" in cfg:
@@ -165,5 +175,7 @@ def hot_path_params(cfg):
         pixel_mean=tuple(_get(cfg, "MODEL.PIXEL_MEAN", [123.675, 116.280, 103.530])),
         pixel_std=tuple(_get(cfg, "MODEL.PIXEL_STD", [58.395, 57.120, 57.375])),
         blocks=blocks,
+        swin=SWIN_SIZES[_get(cfg, "MODEL.SWIN.SIZE", "B-22k")]
+        if "swin" in str(_get(cfg, "MODEL.BACKBONE.NAME", "")).lower() else None,
         device=_get(cfg, "MODEL.DEVICE", "cuda"),
     )

@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 2
+#define DVID_ABI_VERSION 3
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -165,6 +165,30 @@ int dvid_cdist_f32(const float* x, float* out, int n, int d, void* stream) {
 int dvid_furthest_point_sampling(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream) {
   if (!dist || !temp || !idx) return DVID_ERR_ARG;
   return dvid::fps_launch(b, n, m, dist, temp, idx, S(stream));
+}
+
+int dvid_swin_rows(float* x, int write_x, const void* add, int add_mode, const float* gamma, const float* beta,
+                   void* out_f16, float* out_f32, int out_mode, int B, int H, int W, int C, int shift, void* stream) {
+  return dvid::swin_rows_launch(x, write_x, add, add_mode, gamma, beta, out_f16, out_f32, out_mode, B, H, W, C, shift,
+                                S(stream));
+}
+
+int dvid_swin_patch_merge(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta,
+                          void* out_f16, void* stream) {
+  if (!x || !gamma || !beta || !out_f16) return DVID_ERR_ARG;
+  return dvid::swin_merge_launch(x, B, H, W, C, gamma, beta, out_f16, S(stream));
+}
+
+int dvid_swin_patch_gather(const float* img, void* out_f16, int B, int H, int W, const float* mean, const float* std,
+                           void* stream) {
+  if (!img || !out_f16 || !mean || !std) return DVID_ERR_ARG;
+  return dvid::swin_patch_gather_launch(img, out_f16, B, H, W, mean, std, S(stream));
+}
+
+int dvid_swin_window_attention(const void* qkv, const float* bias, void* out_f16, int B, int H, int W, int C,
+                               int heads, int shift, void* stream) {
+  if (!qkv || !bias || !out_f16) return DVID_ERR_ARG;
+  return dvid::swin_window_attention_launch(qkv, bias, out_f16, B, H, W, C, heads, shift, S(stream));
 }
 
 }  // extern "C"

@@ -35,7 +35,7 @@ struct ConvGemmParams {
   const float* bias;     // [cout] or nullptr
   const __half* resid;   // NHWC [n_img, resid_h, resid_w, cout] or nullptr; read at (y >> resid_shift, x >> resid_shift)
   int resid_shift, resid_h, resid_w;
-  int relu;
+  int relu;              // activation: 0 none, 1 ReLU, 2 GELU(erf)
   float* out_f32;        // if set: fp32 output [splits][M][cout] by direct stores (GEMM mode), no bias/resid/relu
   long long m_total;     // rows of the GEMM view (n_img * h_out * w_out)
 };
@@ -283,9 +283,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
             }
-            if (p.relu) {
+            if (p.relu == 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            } else if (p.relu == 2) {   // GELU (erf form, torch.nn.GELU default) - Swin MLP, swintransformer.py:47-66
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {

@@ -69,6 +69,16 @@ int nms_launch(const float* boxes, const float* scores, const int* labels, const
 int cdist_launch(const float* x, float* out, int n, int d, cudaStream_t stream);
 int fps_launch(int b, int n, int m, const float* dist, float* temp, int* idx, cudaStream_t stream);
 
+int swin_rows_launch(float* X, int write_x, const void* add, int add_mode, const float* gamma, const float* beta,
+                     void* out16, float* out32, int out_mode, int B, int H, int W, int C, int shift,
+                     cudaStream_t stream);
+int swin_merge_launch(const float* X, int B, int H, int W, int C, const float* gamma, const float* beta, void* out,
+                      cudaStream_t stream);
+int swin_patch_gather_launch(const float* img, void* out, int B, int H, int W, const float* mean, const float* std,
+                             cudaStream_t stream);
+int swin_window_attention_launch(const void* qkv, const float* bias, void* out, int B, int H, int W, int C, int heads,
+                                 int shift, cudaStream_t stream);
+
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? DVID_OK : DVID_ERR_CUDA; }
 
 }  // namespace dvid

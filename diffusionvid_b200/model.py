@@ -70,7 +70,11 @@ class DiffusionDet(nn.Module):
         self.size_divisibility = 32
         self.noise = None          # optional NoiseSource-like object: get(kind, video, key_frame, index, frames)
         self.demo = False
-        sd = synth.make_state_dict(seed=init_seed, blocks=hp["blocks"], num_heads=hp["num_heads"],
+        self.swin = hp.get("swin")
+        if self.swin is not None and (self.swin["embed"] % 128 != 0 or
+                                      any(self.swin["embed"] * 2 ** i != 32 * h for i, h in enumerate(self.swin["heads"]))):
+            raise DvidError("the sm_100a Swin kernels need embed_dim % 128 == 0 and head dim 32 (Swin-B)")
+        sd = synth.make_state_dict(seed=init_seed, blocks=hp["blocks"], swin=self.swin, num_heads=hp["num_heads"],
                                    num_heads_local=hp["num_heads_local"], ncls=hp["num_classes"],
                                    num_cls=hp["num_cls"], num_reg=hp["num_reg"], global_enable=hp["global_enable"])
         for k, v in sd.items():
@@ -131,12 +135,14 @@ class DiffusionDet(nn.Module):
             return wf, shift.contiguous()
 
         p = "backbone.bottom_up."
-        wf, b = conv_bn(p + "stem.conv1")                        # [64][7][7][3]
+        if self.swin is not None:
+            self._pack_swin(sd, pk, dev)
+        wf, b = conv_bn(p + "stem.conv1") if self.swin is None else (torch.zeros(64, 7, 7, 3, device=dev), None)
         wk = torch.zeros(64, 7, 8, 8, device=dev)
         wk[:, :, :7, :3] = wf
         pk["stem"] = (wk.view(64, -1).to(H).contiguous(), b)
         blocks = []
-        for si, nb in enumerate(hp["blocks"]):
+        for si, nb in enumerate(hp["blocks"] if self.swin is None else ()):
             for bi in range(nb):
                 bn = "%sres%d.%d." % (p, si + 2, bi)
                 e = {"stride": 2 if (bi == 0 and si > 0) else 1}
@@ -145,7 +151,7 @@ class DiffusionDet(nn.Module):
                         wf, b = conv_bn(bn + c)
                         e[c] = (wf.view(wf.shape[0], -1).to(H).contiguous(), b, wf.shape[0], wf.shape[1])
                 blocks.append((si, e))
-        pk["blocks"] = blocks
+        pk["blocks"] = blocks if self.swin is None else []
         for lvl in (3, 4, 5):
             for kind in ("lateral", "output"):
                 n = "backbone.fpn_%s%d" % (kind, lvl)
@@ -206,10 +212,93 @@ class DiffusionDet(nn.Module):
         return pk
 
     # ------------------------------------------------------------------------------------------ backbone
+    def _pack_swin(self, sd, pk, dev):
+        """Swin weights in kernel layouts: fp16 [out][in] linears, dense per-head relative position bias
+        (table[relative_position_index], swintransformer.py:160-163), fp32 LayerNorm params."""
+        cfgs = self.swin
+        p = "backbone.bottom_up."
+        ws = 7
+        coords = torch.stack(torch.meshgrid([torch.arange(ws), torch.arange(ws)], indexing="ij")).flatten(1)
+        rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+        rel[:, :, 0] += ws - 1; rel[:, :, 1] += ws - 1; rel[:, :, 0] *= 2 * ws - 1
+        rpi = rel.sum(-1).view(-1).to(dev)
+
+        def lnp(n):
+            return (sd[n + ".weight"].contiguous(), sd[n + ".bias"].contiguous())
+
+        def lin(n, bias=True):
+            return (sd[n + ".weight"].to(H).contiguous(), sd[n + ".bias"].contiguous() if bias else None)
+
+        E = cfgs["embed"]
+        w = torch.zeros(E, 64, device=dev)
+        w[:, :48] = sd[p + "patch_embed.proj.weight"].reshape(E, 48)
+        sw = {"pe": (w.to(H).contiguous(), sd[p + "patch_embed.proj.bias"].contiguous()),
+              "pe_norm": lnp(p + "patch_embed.norm"), "stages": []}
+        for i, (d, nh) in enumerate(zip(cfgs["depths"], cfgs["heads"])):
+            st = {"C": E * 2 ** i, "heads": nh, "blocks": []}
+            for b in range(d):
+                pre = "%slayers.%d.blocks.%d." % (p, i, b)
+                tbl = sd[pre + "attn.relative_position_bias_table"]
+                st["blocks"].append(dict(
+                    n1=lnp(pre + "norm1"), qkv=lin(pre + "attn.qkv"), proj=lin(pre + "attn.proj"),
+                    bias=tbl[rpi].view(ws * ws, ws * ws, nh).permute(2, 0, 1).contiguous(),
+                    n2=lnp(pre + "norm2"), fc1=lin(pre + "mlp.fc1"), fc2=lin(pre + "mlp.fc2"),
+                    shift=0 if b % 2 == 0 else ws // 2))
+            if i < len(cfgs["depths"]) - 1:
+                pre = "%slayers.%d.downsample." % (p, i)
+                st["down"] = (lnp(pre + "norm"), lin(pre + "reduction", bias=False)[0])
+            if i >= 1:
+                st["out_norm"] = lnp("%snorm%d" % (p, i))
+            sw["stages"].append(st)
+        pk["swin"] = sw
+
+    def _swin_body(self, imgs):
+        """SwinTransformer.forward (swintransformer.py:621-648) -> [swin1, swin2, swin3] NHWC fp16."""
+        pk = self._pk
+        sw = pk["swin"]
+        B, _, Hh, Ww = imgs.shape
+        tok = ops.swin_patch_gather(imgs.contiguous(), pk["mean"], pk["std"])
+        y = ops.gemm(tok, sw["pe"][0], sw["pe"][1])
+        Ht, Wt = Hh // 4, Ww // 4
+        C = sw["stages"][0]["C"]
+        _, X = ops.swin_rows(B, Ht, Wt, C, add=y, add_mode=1, ln=sw["pe_norm"], out_f32=True)
+        outs = []
+        for st in sw["stages"]:
+            C, nh = st["C"], st["heads"]
+            pend = None        # fc2 output of the previous block, not yet added to X
+            for blk in st["blocks"]:
+                sh = blk["shift"]
+                xw, _ = ops.swin_rows(B, Ht, Wt, C, x=X, write_x=pend is not None, add=pend,
+                                      add_mode=1 if pend is not None else 0, ln=blk["n1"], out_f16=True, out_mode=2,
+                                      shift=sh)
+                qkv = ops.gemm(xw, blk["qkv"][0], blk["qkv"][1])
+                ao = ops.swin_window_attention(qkv, blk["bias"], B, Ht, Wt, C, nh, sh)
+                pr = ops.gemm(ao, blk["proj"][0], blk["proj"][1])
+                y, _ = ops.swin_rows(B, Ht, Wt, C, x=X, write_x=True, add=pr, add_mode=2, ln=blk["n2"], out_f16=True,
+                                     shift=sh)
+                hdn = ops.gemm(y, blk["fc1"][0], blk["fc1"][1], relu=2)
+                pend = ops.gemm(hdn, blk["fc2"][0], blk["fc2"][1])
+            if "out_norm" in st:
+                f, _ = ops.swin_rows(B, Ht, Wt, C, x=X, write_x=True, add=pend, add_mode=1, ln=st["out_norm"],
+                                     out_f16=True)
+                outs.append(f.view(B, Ht, Wt, C))
+            else:
+                ops.swin_rows(B, Ht, Wt, C, x=X, write_x=True, add=pend, add_mode=1)
+            if "down" in st:
+                m = ops.swin_patch_merge(X, st["down"][0])
+                part, _ = ops.gemm_partials(m, st["down"][1], 1)
+                Ht, Wt = (Ht + 1) // 2, (Wt + 1) // 2
+                X = part[0].view(B, Ht, Wt, 2 * C)
+        return outs
+
     def extract_features(self, imgs):
-        """imgs [n,3,Hp,Wp] fp32 in [0,1] on the device -> [p3,p4,p5] NHWC fp16 (detectron2 R-101 + FPN)."""
+        """imgs [n,3,Hp,Wp] fp32 in [0,1] on the device -> [p3,p4,p5] NHWC fp16 (detectron2 R-101 + FPN, SURVEY A1, or
+        Swin + FPN, swintransformer.py:735-751)."""
         pk = self._pk or self._pack()
         n, _, Hh, Ww = imgs.shape
+        if self.swin is not None:
+            c3, c4, c5 = self._swin_body(imgs)
+            return self._fpn(c3, c4, c5)
         x = ops.preprocess(imgs.contiguous(), pk["mean"], pk["std"], halo=3)
         x = ops.stem_conv(x, pk["stem"][0], pk["stem"][1], n, Hh, Ww, 64, relu=True)
         x = ops.maxpool3x3s2(x)
@@ -228,6 +317,12 @@ class DiffusionDet(nn.Module):
             w, b, co, _ = e["conv3"]
             x = ops.conv2d(y, w, b, co, 1, 1, 1, 0, relu=True, resid=sc)
             outs[si] = x
+        return self._fpn(outs[1], outs[2], outs[3])
+
+    def _fpn(self, c3, c4, c5):
+        """detectron2 FPN: lateral 1x1 + nearest x2 top-down sum (fused into the lateral epilogue) + 3x3."""
+        pk = self._pk
+        outs = {1: c3, 2: c4, 3: c5}
         w, b, _ = pk["backbone.fpn_lateral5"]
         prev = ops.conv2d(outs[3], w, b, 256, 1, 1, 1, 0, relu=False)
         w, b, _ = pk["backbone.fpn_output5"]

@@ -90,7 +90,7 @@ def stem_conv(x_haloed, w, bias, n, H_, W_, cout, relu=True, out=None):
 
 
 def gemm(a, w, bias=None, relu=False, resid=None, out=None):
-    """fp16 out: act(a @ w^T + bias + resid)."""
+    """fp16 out: act(a @ w^T + bias + resid); relu: False/0 none, True/1 ReLU, 2 GELU(erf)."""
     _chk(a, H, "a"); _chk(w, H, "w"); _chk(bias, F32, "bias"); _chk(resid, H, "resid")
     m, k = a.shape
     n = w.shape[0]
@@ -324,6 +324,58 @@ def nms(boxes, scores, labels=None, counts=None, n=None, thr=0.5, plus_one=False
                               cur_stream()), "dvid_nms")
     _cnt()
     return dict(keep=keep, count=count, boxes=ob, scores=os_, labels=ol)
+
+
+# ------------------------------------------------------------------------------------------------ Swin backbone
+def swin_rows(B, Hh, W, C, x=None, write_x=False, add=None, add_mode=0, ln=None, out_f16=False, out_f32=False,
+              out_mode=1, shift=0):
+    """Row kernel over the fp32 residual stream (see dvid_swin_rows in include/dvid_b200.h).  Returns (out16, out32)."""
+    _chk(x, F32, "x"); _chk(add, H, "add")
+    g, b = ln if ln is not None else (None, None)
+    _chk(g, F32, "gamma"); _chk(b, F32, "beta")
+    dev = x.device if x is not None else add.device
+    o16 = o32 = None
+    if out_f16:
+        rows = B * ((Hh + 6) // 7) * ((W + 6) // 7) * 49 if out_mode == 2 else B * Hh * W
+        o16 = torch.empty((rows, C), device=dev, dtype=H)
+    if out_f32:
+        o32 = torch.empty((B, Hh, W, C), device=dev, dtype=F32)
+    check(_lib.lib().dvid_swin_rows(ptr(x), int(write_x), ptr(add), add_mode, ptr(g), ptr(b), ptr(o16), ptr(o32),
+                                    out_mode, B, Hh, W, C, shift, cur_stream()), "dvid_swin_rows")
+    _cnt()
+    return o16, o32
+
+
+def swin_patch_merge(x, ln):
+    _chk(x, F32, "x")
+    B, Hh, W, C = x.shape
+    out = torch.empty((B * ((Hh + 1) // 2) * ((W + 1) // 2), 4 * C), device=x.device, dtype=H)
+    check(_lib.lib().dvid_swin_patch_merge(ptr(x), B, Hh, W, C, ptr(ln[0]), ptr(ln[1]), ptr(out), cur_stream()),
+          "dvid_swin_patch_merge")
+    _cnt()
+    return out
+
+
+def swin_patch_gather(img, mean, std):
+    _chk(img, F32, "img")
+    B, _, Hh, W = img.shape
+    out = torch.empty((B * (Hh // 4) * (W // 4), 64), device=img.device, dtype=H)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    check(_lib.lib().dvid_swin_patch_gather(ptr(img), ptr(out), B, Hh, W, m, s, cur_stream()), "dvid_swin_patch_gather")
+    _cnt()
+    return out
+
+
+def swin_window_attention(qkv, bias, B, Hh, W, C, heads, shift):
+    _chk(qkv, H, "qkv"); _chk(bias, F32, "bias")
+    out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=H)
+    nw = B * ((Hh + 6) // 7) * ((W + 6) // 7)
+    with _prof("attention", 4.0 * nw * heads * 49 * 49 * 32, 2.0 * qkv.numel() + 2.0 * out.numel()):
+        check(_lib.lib().dvid_swin_window_attention(ptr(qkv), ptr(bias), ptr(out), B, Hh, W, C, heads, shift,
+                                                    cur_stream()), "dvid_swin_window_attention")
+    _cnt()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ global memory

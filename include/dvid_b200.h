@@ -45,7 +45,8 @@ DVID_API int dvid_num_sms(void);
  * mega_core/modeling/detector/diffusion_det.py:219 and calls at :427 (FrozenBN folded into weight/bias by the host).
  *   out[n,y,x,co] = act( bias[co] + sum_{r,s,ci} in[n, y*stride+r-pad, x*stride+s-pad, ci] * weight[co,(r*S+s)*Cin+ci]
  *                        + resid[n, y>>resid_shift, x>>resid_shift, co] )
- * resid_shift=1 implements FPN's nearest x2 top-down addition. bias/resid may be NULL. relu: 0/1.
+ * resid_shift=1 implements FPN's nearest x2 top-down addition. bias/resid may be NULL.
+ * relu: activation 0 none / 1 ReLU / 2 GELU(erf) (same meaning in dvid_gemm_f16).
  * Requirements: Cin % 8 == 0, Cout % 8 == 0, stride in {1,2}.
  */
 DVID_API int dvid_conv2d_nhwc_f16(const void* in, const void* weight, const float* bias, const void* resid, void* out,
@@ -162,6 +163,32 @@ DVID_API int dvid_cdist_f32(const float* x, float* out, int n, int d, void* stre
 /* Drop-in for mega_core._C.furthest_point_sampling (mega_core/csrc/fps.h:15-36, cuda/fps.cu:25-185): dist (b,n,n) fp32,
  * temp (b,n) pre-filled with 1e10, idx (b,m) int32; identical picks including the kernel's tie-breaking. */
 DVID_API int dvid_furthest_point_sampling(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Swin Transformer backbone (mega_core/modeling/backbone/swintransformer.py), csrc/swin.cu.  The linear layers
+ * (qkv / proj / fc1+GELU / fc2 / reduction / patch-embed projection) are dvid_gemm_f16 calls.
+ */
+/* Row kernel over the fp32 residual stream x [B][H][W][C] (C % 128 == 0, C <= 2048):
+ *   v = x[token] (0 if x == NULL) + add[...]      add fp16 rows; add_mode 0 none / 1 token order / 2 shifted-window order
+ *                                                 (window_reverse + roll(+shift) + crop, swintransformer.py:259-270)
+ *   x[token] = v if write_x;  y = LayerNorm(v; gamma, beta, eps 1e-5) (y = v if gamma == NULL)
+ *   out_f32[token] = y;  out_f16[row] = y with out_mode 1 token order / 2 shifted-window order including zero rows
+ *   for the padding to a multiple of 7 (F.pad + roll(-shift) + window_partition, :236-252).  shift: 0 or 3. */
+DVID_API int dvid_swin_rows(float* x, int write_x, const void* add, int add_mode, const float* gamma, const float* beta,
+                   void* out_f16, float* out_f32, int out_mode, int B, int H, int W, int C, int shift, void* stream);
+/* PatchMerging (:279-317): out_f16 [B*ceil(H/2)*ceil(W/2)][4C] = LayerNorm_4C(cat of the 2x2 neighbours, zero padded). */
+DVID_API int dvid_swin_patch_merge(const float* x, int B, int H, int W, int C, const float* gamma, const float* beta,
+                          void* out_f16, void* stream);
+/* normalizer (diffusion_det.py:301-303) + 4x4 patch extraction for PatchEmbed (:422-461): img [B][3][H][W] fp32 ->
+ * out_f16 [B*(H/4)*(W/4)][64], k = c*16 + py*4 + px, k >= 48 zero.  mean/std: 3 host floats (already / 255). */
+DVID_API int dvid_swin_patch_gather(const float* img, void* out_f16, int B, int H, int W, const float* mean,
+                           const float* std, void* stream);
+/* WindowAttention core (:145-176): softmax(q*scale k^T + bias + shift mask) v per (window, head), head dim 32.
+ * qkv [windows*49][3C] fp16 in shifted-window order, bias [heads][49][49] fp32 (table gathered by
+ * relative_position_index), out_f16 [windows*49][C].  The SW-MSA mask of BasicLayer.forward (:387-406) is derived from
+ * the token coordinates.  H, W: token grid of the stage (unpadded). */
+DVID_API int dvid_swin_window_attention(const void* qkv, const float* bias, void* out_f16, int B, int H, int W, int C,
+                               int heads, int shift, void* stream);
 
 #ifdef __cplusplus
 }

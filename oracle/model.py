@@ -395,6 +395,9 @@ class OracleDiffusionVID:
     def backbone(self, imgs):
         mean = torch.tensor(self.cfg["pixel_mean"]).view(1, 3, 1, 1) / 255.
         std = torch.tensor(self.cfg["pixel_std"]).view(1, 3, 1, 1) / 255.
+        if "backbone.bottom_up.patch_embed.proj.weight" in self.c.sd:      # vid_Swin_B_DiffusionVID.yaml
+            from . import swin
+            return swin.swin_fpn(self.c, (imgs - mean) / std)
         return resnet_fpn(self.c, (imgs - mean) / std)
 
     def forward(self, s):
