@@ -11,6 +11,7 @@
 // TMA, which implements the convolution's zero padding and all tile tails without any predicate in the kernel.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM -> regs -> swizzled smem ->
 // TMA store). Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+#include <stdlib.h>
 #include "ptx_sm100.cuh"
 #include "dvid_internal.h"
 
@@ -38,34 +39,59 @@ struct ConvGemmParams {
   int relu;              // activation: 0 none, 1 ReLU, 2 GELU(erf)
   float* out_f32;        // if set: fp32 output [splits][M][cout] by direct stores (GEMM mode), no bias/resid/relu
   long long m_total;     // rows of the GEMM view (n_img * h_out * w_out)
+  int dbg;               // DVID_DBG experiment bits (timing experiments only; results are wrong when set)
+  unsigned long long* trace;   // DVID_TRACE: per-role event log of CTA 0 (debug only), else nullptr
 };
 
-template <int BN>
+// BSTAT ("B-stationary", K <= 256): the whole [BN x K] weight tile stays resident in smem while the CTA walks a
+// contiguous range of M tiles (m fastest), so the weights are read from L2 once per CTA instead of once per tile and
+// only the A tiles stream through the ring.  L2->SM bandwidth (~6.5 TB/s for unique lines) is what bounds the short-K
+// GEMMs (dynamic_layer 2400x256->32768: 467 MB of operand reads at 128x256 tiles -> ~190 MB).
+constexpr int BSTAT_MAX_KB = 4;   // K <= 256
+// named barriers: 1 = the four epilogue warps; FULL/FREE = epilogue warps <-> TMA store warp, per staging buffer
+constexpr int BAR_FULL0 = 2, BAR_FREE0 = 4;
+
+template <int BN, bool BSTAT = false>
 struct ConvGemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int STAGES = BSTAT ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr int RING_BYTES =
+      BSTAT ? (STAGES * A_STAGE_BYTES + BSTAT_MAX_KB * B_STAGE_BYTES) : (STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
   static constexpr int SMEM_BYTES =
-      STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-      BN * 4 /*bias staging*/;
+      RING_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias staging*/;
 };
 
-template <int BN>
+// debug event log (DVID_TRACE=1): role r appends (code, clock) pairs to its own 1024-entry lane of p.trace, CTA 0 only
+__device__ __forceinline__ void trace_ev(const ConvGemmParams& p, int role, int& n, unsigned code) {
+  if (p.trace != nullptr && blockIdx.x == 0 && n < 1023) {
+    const unsigned long long t = static_cast<unsigned long long>(clock64());   // SM-local cycles (cheap)
+    p.trace[role * 2048 + 2 * n] = code;
+    p.trace[role * 2048 + 2 * n + 1] = t;
+    ++n;
+  }
+}
+
+template <int BN, bool BSTAT>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BN>;
+  using Cfg = ConvGemmCfg<BN, BSTAT>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align to 1024 B (128-byte swizzle atoms) with pointer arithmetic on the __shared__ symbol, so the compiler keeps
+  // the shared state space (LDS/STS instead of generic LD/ST in the epilogue)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
-  uint8_t* sOut = sB + STAGES * Cfg::B_STAGE_BYTES;
+  uint8_t* sB = sA + STAGES * A_STAGE_BYTES;      // ring (normal) or the resident [kb][BN x 64] weight tile (BSTAT)
+  uint8_t* sOut = smem + Cfg::RING_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + 2 * OUT_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* bres_full = tmem_empty + 2;           // BSTAT: resident weights landed / may be overwritten
+  uint64_t* bres_empty = bres_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_empty + 1);
   float* sBias = reinterpret_cast<float*>(sOut + 2 * OUT_STAGE_BYTES + 256);   // [BN] bias of the current tile
 
   const int warp = threadIdx.x >> 5;
@@ -85,6 +111,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
     }
+    mbar_init(bres_full, 1);
+    mbar_init(bres_empty, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -95,17 +123,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int tw = 1 << p.tw_log2;
+  // tile walk: normal = strided over the grid, n fastest; BSTAT = one contiguous range per CTA, m fastest (splits == 1)
+  const int tile_begin = BSTAT ? static_cast<int>(static_cast<long long>(total_tiles) * blockIdx.x / gridDim.x)
+                               : static_cast<int>(blockIdx.x);
+  const int tile_end = BSTAT ? static_cast<int>(static_cast<long long>(total_tiles) * (blockIdx.x + 1) / gridDim.x)
+                             : total_tiles;
+  const int tile_step = BSTAT ? 1 : static_cast<int>(gridDim.x);
+  auto decode = [&](int tile, int& n_idx, int& m_idx, int& split) {
+    if (BSTAT) {
+      n_idx = tile / p.m_tiles;
+      m_idx = tile - n_idx * p.m_tiles;
+      split = 0;
+    } else {
+      n_idx = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      m_idx = rest % p.m_tiles;
+      split = rest / p.m_tiles;
+    }
+  };
 
   if (warp == 0) {
     if (elect_one()) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_idx = tile % p.n_tiles;
-        const int rest = tile / p.n_tiles;
-        const int m_idx = rest % p.m_tiles;
-        const int split = rest / p.m_tiles;
+      int cur_n = -1;
+      uint32_t bphase = 0;
+      int tn = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        int n_idx, m_idx, split;
+        decode(tile, n_idx, m_idx, split);
         const int tx = m_idx % p.tiles_x;
         const int ty = (m_idx / p.tiles_x) % p.tiles_y;
         const int img = m_idx / (p.tiles_x * p.tiles_y);
@@ -113,16 +160,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int y_in0 = ty * p.th * p.stride - p.pad;
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+        if (BSTAT && n_idx != cur_n) {
+          if (cur_n >= 0) {                       // every MMA that reads the old weights has completed
+            mbar_wait(bres_empty, bphase);
+            bphase ^= 1;
+          }
+          cur_n = n_idx;
+          mbar_expect_tx(bres_full, p.total_kb * Cfg::B_STAGE_BYTES);
+          for (int kb = 0; kb < p.total_kb; ++kb) {
+            const int tap = kb / p.kb_per_tap;
+            const int cblk = kb - tap * p.kb_per_tap;
+            tma_load_2d(sB + kb * Cfg::B_STAGE_BYTES, &tmB, bres_full, tap * p.cin + cblk * BLOCK_K, n_idx * BN);
+          }
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           const int tap = kb / p.kb_per_tap;
           const int cblk = kb - tap * p.kb_per_tap;
           const int r = tap / p.S;
           const int s = tap - r * p.S;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+          trace_ev(p, 0, tn, (tile << 8) | kb);     // slot free, load issued
+          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (BSTAT ? 0 : Cfg::B_STAGE_BYTES));
           tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cblk * BLOCK_K, x_in0 + s, y_in0 + r, img);
-          tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], tap * p.cin + cblk * BLOCK_K,
-                      n_idx * BN);
+          if (!BSTAT)
+            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], tap * p.cin + cblk * BLOCK_K,
+                        n_idx * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -134,31 +196,87 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int split = (tile / p.n_tiles) / p.m_tiles;
+    int cur_n = -1;
+    uint32_t bphase = 0;
+    int tn = 0;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      int n_idx, m_idx, split;
+      decode(tile, n_idx, m_idx, split);
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+      if (BSTAT && n_idx != cur_n) {
+        cur_n = n_idx;
+        mbar_wait(bres_full, bphase);
+        bphase ^= 1;
+      }
+      bool last_of_n = false;
+      if (BSTAT) {
+        const int nt = tile + tile_step;
+        last_of_n = (nt < tile_end) && (nt / p.m_tiles != n_idx);
+      }
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
+      if (lane == 0) trace_ev(p, 1, tn, (tile << 8) | 0xff);   // accumulator stage free
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (lane == 0) trace_ev(p, 1, tn, (tile << 8) | kb);     // operands landed, MMAs issued
         if (elect_one()) {
           const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(sA + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+          const uint64_t bdesc =
+              umma_desc_sw128_kmajor(smem_u32(sB + (BSTAT ? kb : stage) * Cfg::B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
             umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == kb_end - 1) umma_commit(&tmem_full[as]);
+          if (kb == kb_end - 1) {
+            umma_commit(&tmem_full[as]);
+            if (last_of_n) umma_commit(bres_empty);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp == 3) {
+    // ===================== TMA store warp =====================
+    // Takes the staged 128x64 fp16 chunks from the epilogue warps (named barriers FULL0/1) and issues the TMA stores, so
+    // the store issue + the wait for the staging buffer to drain are off the epilogue's critical path.
+    if (p.out_f32 == nullptr && !(p.dbg & 16)) {
+      int total_chunks = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        int n_idx, m_idx, split;
+        decode(tile, n_idx, m_idx, split);
+        total_chunks += min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
+      }
+      int g = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        int n_idx, m_idx, split;
+        decode(tile, n_idx, m_idx, split);
+        const int tx = m_idx % p.tiles_x;
+        const int ty = (m_idx / p.tiles_x) % p.tiles_y;
+        const int img = m_idx / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * tw, y0 = ty * p.th;
+        const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const int sb = g & 1;
+          named_bar_sync(BAR_FULL0 + sb, 160);
+          if (lane == 0 && !(p.dbg & 1)) {
+            tma_store_4d(&tmC, sOut + sb * OUT_STAGE_BYTES, n_idx * BN + c * 64, x0, y0, img);
+            tma_store_commit();
+          }
+          if (g >= 1 && g + 1 < total_chunks) {     // chunk g+1 will reuse the buffer of chunk g-1
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            named_bar_arrive(BAR_FREE0 + (sb ^ 1), 160);
+          }
+        }
+      }
+      if (lane == 0) tma_store_wait<0>();
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -168,25 +286,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 4;  // == warp % 4: the TMEM sub-partition this warp may read
     const int row = ew * 32 + lane;
     const int et = threadIdx.x - 128;
-    const bool store_leader = (threadIdx.x == 128);
     int staged = 0;
     int as = 0;
     uint32_t aphase = 0;
+    int tn = 0;
     float bnext[BN / 128 > 0 ? BN / 128 : 1];
     auto fetch_bias = [&](int tile) {
-      const int n0 = (tile % p.n_tiles) * BN;
+      int bn_idx, bm_idx, bsplit;
+      decode(tile, bn_idx, bm_idx, bsplit);
+      const int n0 = bn_idx * BN;
 #pragma unroll
       for (int i = 0; i < (BN + 127) / 128; ++i) {
         const int col = n0 + et + i * 128;
         bnext[i] = (p.bias != nullptr && (BN >= 128 || et < BN) && col < p.cout) ? __ldg(p.bias + col) : 0.f;
       }
     };
-    if (blockIdx.x < total_tiles && p.out_f32 == nullptr) fetch_bias(blockIdx.x);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_idx = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
-      const int m_idx = rest % p.m_tiles;
-      const int split = rest / p.m_tiles;
+    if (tile_begin < tile_end && p.out_f32 == nullptr) fetch_bias(tile_begin);
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      int n_idx, m_idx, split;
+      decode(tile, n_idx, m_idx, split);
       const int tx = m_idx % p.tiles_x;
       const int ty = (m_idx / p.tiles_x) % p.tiles_y;
       const int img = m_idx / (p.tiles_x * p.tiles_y);
@@ -215,6 +333,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
+      if (et == 0) trace_ev(p, 2, tn, (tile << 8) | 0xfe);       // accumulator ready
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
 
       if (p.out_f32 != nullptr) {
@@ -239,37 +358,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
-        // stage this tile's bias (all epilogue threads passed the last barrier of the previous tile, so nobody still
-        // reads the old values), then start fetching the next tile's.
+        // stage this tile's bias: the barrier below orders the previous tile's last sBias reads before these writes and
+        // these writes before this tile's reads.  Then start fetching the next tile's bias.
+        if (!(p.dbg & 64)) {
+          named_bar_sync(1, 128);
 #pragma unroll
-        for (int i = 0; i < (BN + 127) / 128; ++i)
-          if (BN >= 128 || et < BN) sBias[et + i * 128] = bnext[i];
-        if (tile + static_cast<int>(gridDim.x) < total_tiles) fetch_bias(tile + gridDim.x);
+          for (int i = 0; i < (BN + 127) / 128; ++i)
+            if (BN >= 128 || et < BN) sBias[et + i * 128] = bnext[i];
+          if (tile + tile_step < tile_end) fetch_bias(tile + tile_step);
+          named_bar_sync(1, 128);
+        }
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
-          const int ch0 = n_idx * BN + c * 64;
-          uint8_t* buf = sOut + (staged & 1) * OUT_STAGE_BYTES;
+          const int sb = staged & 1;
+          uint8_t* buf = sOut + sb * OUT_STAGE_BYTES;
           uint4 rcur[8];
           if (p.resid != nullptr) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
             if (c + 1 < nchunks) fetch_resid(c + 1);
           }
-          if (store_leader) tma_store_wait_read<1>();  // the store that last read this buffer has drained it
-          named_bar_sync(1, 128);                      // also publishes sBias
+          uint32_t v[2][32];
+          if (!(p.dbg & 2)) {
+            tmem_ld32(tbase + c * 64, v[0]);
+            tmem_ld32(tbase + c * 64 + 32, v[1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[0][j] = v[1][j] = 0u;
+          }
+          // the store warp has drained the TMA store that last read this staging buffer (two chunks ago)
+          if (staged >= 2 && !(p.dbg & 16)) named_bar_sync(BAR_FREE0 + sb, 160);
+          if (!(p.dbg & 2)) tmem_ld_wait();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld32(tbase + c * 64 + h * 32, v);
-            tmem_ld_wait();
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sBias + c * 64 + h * 32 + j);
-              f[j] = __uint_as_float(v[j]) + b4.x;
-              f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-              f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+              const float4 b4 = (p.dbg & 8) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                            : *reinterpret_cast<const float4*>(sBias + c * 64 + h * 32 + j);
+              f[j] = __uint_as_float(v[h][j]) + b4.x;
+              f[j + 1] = __uint_as_float(v[h][j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[h][j + 2]) + b4.z;
+              f[j + 3] = __uint_as_float(v[h][j + 3]) + b4.w;
             }
             if (p.resid != nullptr) {
 #pragma unroll
@@ -290,6 +420,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
             }
+            if (p.dbg & 4) {     // experiment: no conversion / staging (keep the values alive)
+              float acc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc += f[j];
+              if (acc == 123.456f) buf[row] = 1;
+              continue;
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 pk;
@@ -301,12 +438,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *reinterpret_cast<uint4*>(buf + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
             }
           }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (store_leader) {
-            tma_store_4d(&tmC, buf, ch0, x0, y0, img);
-            tma_store_commit();
-          }
+          if (!(p.dbg & 32)) fence_proxy_async_smem();
+          if (!(p.dbg & 16)) named_bar_arrive(BAR_FULL0 + sb, 160);   // hand the staged chunk to the store warp
+          if (et == 0) trace_ev(p, 2, tn, (tile << 8) | c);
           ++staged;
         }
       }
@@ -315,7 +449,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (store_leader) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -384,20 +517,43 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN>
+template <int BN, bool BSTAT>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p,
                       cudaStream_t stream) {
-  using Cfg = ConvGemmCfg<BN>;
+  using Cfg = ConvGemmCfg<BN, BSTAT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, BSTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return DVID_ERR_CUDA;
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  conv_gemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  if (getenv("DVID_TRACE") != nullptr) {     // debug: run once with the event log and print it (synchronises!)
+    ConvGemmParams q = p;
+    const size_t bytes = 3 * 2048 * sizeof(unsigned long long);
+    cudaMalloc(&q.trace, bytes);
+    cudaMemsetAsync(q.trace, 0, bytes, stream);
+    conv_gemm_kernel<BN, BSTAT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, q);
+    cudaStreamSynchronize(stream);
+    static unsigned long long host[3 * 2048];
+    cudaMemcpy(host, q.trace, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(q.trace);
+    unsigned long long t0 = ~0ull;
+    for (int r = 0; r < 3; ++r)
+      if (host[r * 2048 + 1] && host[r * 2048 + 1] < t0) t0 = host[r * 2048 + 1];
+    fprintf(stderr, "dvid trace BN=%d bstat=%d tiles=%d grid=%d total_kb=%d\n", BN, (int)BSTAT, total, grid, p.total_kb);
+    const char* names[3] = {"load", "mma ", "epi "};
+    for (int r = 0; r < 3; ++r)
+      for (int i = 0; i < 1023 && host[r * 2048 + 2 * i + 1]; ++i) {
+        if (i > 60) break;
+        fprintf(stderr, "  %s tile %4llu ev %3llu  t=%8.2f us\n", names[r], host[r * 2048 + 2 * i] >> 8,
+                host[r * 2048 + 2 * i] & 0xff, (host[r * 2048 + 2 * i + 1] - t0) / 1900.0);
+      }
+    return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
+  }
+  conv_gemm_kernel<BN, BSTAT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
 }
 
@@ -448,6 +604,12 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   p.relu = relu;
   p.out_f32 = out_f32;
   p.m_total = static_cast<long long>(n) * p.h_out * p.w_out;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("DVID_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+    p.trace = nullptr;
+  }
   if (out_f32 != nullptr && !(p.h_out == 1 && n == 1 && p.th == 1)) return DVID_ERR_SHAPE;  // GEMM view only
 
   int bn = force_bn;
@@ -492,9 +654,18 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     if (out_f32 == nullptr) return DVID_ERR_SHAPE;
     tmC = tmA;  // unused by the fp32 path
   }
-  if (bn == 256) return launch_cfg<256>(tmA, tmB, tmC, p, stream);
-  if (bn == 128) return launch_cfg<128>(tmA, tmB, tmC, p, stream);
-  return launch_cfg<64>(tmA, tmB, tmC, p, stream);
+  // weight-stationary walk when the whole K fits (<= 256) and every CTA gets several tiles of the same weight tile
+  static int bstat_env = -1;
+  if (bstat_env < 0) { const char* e = getenv("DVID_BSTAT"); bstat_env = e ? atoi(e) : 1; }
+  const bool bstat = bstat_env && out_f32 == nullptr && p.total_kb <= BSTAT_MAX_KB && bn >= 128 &&
+                     static_cast<long long>(p.m_tiles) * p.n_tiles >= 2LL * num_sms();
+  if (bstat) {
+    if (bn == 256) return launch_cfg<256, true>(tmA, tmB, tmC, p, stream);
+    return launch_cfg<128, true>(tmA, tmB, tmC, p, stream);
+  }
+  if (bn == 256) return launch_cfg<256, false>(tmA, tmB, tmC, p, stream);
+  if (bn == 128) return launch_cfg<128, false>(tmA, tmB, tmC, p, stream);
+  return launch_cfg<64, false>(tmA, tmB, tmC, p, stream);
 }
 
 // Stem convolution 7x7 / stride 2 / pad 3 with 3 input channels (detectron2 BasicStem) as an implicit

@@ -132,3 +132,35 @@ def test_conv_stride2_tma(cuda, n, h, w, cin, cout, R, pad):
     assert not torch.isnan(out).any()
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("m,n,k", [(2400, 32768, 256), (2400, 4096, 128), (5000, 1024, 192), (40000, 256, 64)])
+def test_gemm_weight_stationary_walk(cuda, m, n, k):
+    """shapes that take the B-stationary tile walk (K <= 256, >= 2 tiles per SM): bias + ReLU epilogue, ragged M."""
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    a = (torch.randn(m, k, generator=g) * 0.5).half().to(cuda)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).half().to(cuda)
+    bias = torch.randn(n, generator=g).to(cuda)
+    out = _gemm(a, w, bias, None, relu=1)
+    # reference in chunks of columns to bound memory
+    err, scale = 0.0, 1.0
+    for c0 in range(0, n, 4096):
+        ref = torch.relu(a.float() @ w[c0:c0 + 4096].float().t() + bias[c0:c0 + 4096])
+        err = max(err, (out[:, c0:c0 + 4096].float() - ref).abs().max().item())
+        scale = max(scale, ref.abs().max().item())
+    assert err <= 2e-3 * scale, err
+
+
+def test_conv1x1_weight_stationary_with_residual(cuda):
+    """res4-style conv3: 256 -> 1024 on 8 x 38 x 64 pixels + residual + ReLU (152 x 4 tiles -> B-stationary walk)."""
+    g = torch.Generator(device="cpu").manual_seed(23)
+    n, h, w, cin, cout = 8, 38, 64, 256, 1024
+    x = torch.randn(n, h, w, cin, generator=g).half().to(cuda)
+    wt = (torch.randn(cout, cin, generator=g) / cin ** 0.5).half().to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    resid = torch.randn(n, h, w, cout, generator=g).half().to(cuda)
+    out = _conv(x, wt, bias, resid, cout, 1, 1, 1, 0, 0, 1)
+    ref = torch.relu(x.float().view(-1, cin) @ wt.float().t() + bias + resid.float().view(-1, cout)).view(n, h, w, cout)
+    assert not torch.isnan(out).any()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
