@@ -34,6 +34,7 @@ SIGNATURES = {
     "dvid_small_linear": [P, P, P, P, I, I, I, I, I, P],
     "dvid_time_sinusoid": [P, P, P, I, P],
     "dvid_head_final": [P, I, P, I, P, I, P, P, P, P, I, P],
+    "dvid_head_tail": [P, P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, P],
     "dvid_noise_to_boxes": [P, P, I, F, F, F, P],
     "dvid_ddim_step": [P, I, P, P, P, P, P, P, P, I, I, F, F, F, F, F, F, F, F, P],
     "dvid_topk_scores": [P, P, I, I, I, I, P, P, P, I, I, P],

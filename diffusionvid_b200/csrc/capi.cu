@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 3
+#define DVID_ABI_VERSION 4
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -165,6 +165,22 @@ int dvid_cdist_f32(const float* x, float* out, int n, int d, void* stream) {
 int dvid_furthest_point_sampling(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream) {
   if (!dist || !temp || !idx) return DVID_ERR_ARG;
   return dvid::fps_launch(b, n, m, dist, temp, idx, S(stream));
+}
+
+int dvid_head_tail(const void* fc, const void* cls_w, const float* cls_ln_g, const float* cls_ln_b, const void* logit_w,
+                   const float* logit_bias, int C, const void* reg_w0, const void* reg_w1, const void* reg_w2,
+                   const float* reg_ln_g0, const float* reg_ln_b0, const float* reg_ln_g1, const float* reg_ln_b1,
+                   const float* reg_ln_g2, const float* reg_ln_b2, const void* delta_w, const float* delta_bias,
+                   const float* boxes_in, float* logits_out, float* boxes_out, int M, void* stream) {
+  if (!fc || !cls_w || !cls_ln_g || !cls_ln_b || !logit_w || !logit_bias || !reg_w0 || !reg_w1 || !reg_w2 ||
+      !reg_ln_g0 || !reg_ln_b0 || !reg_ln_g1 || !reg_ln_b1 || !reg_ln_g2 || !reg_ln_b2 || !delta_w || !delta_bias ||
+      !boxes_in || !logits_out || !boxes_out)
+    return DVID_ERR_ARG;
+  const void* rw[3] = {reg_w0, reg_w1, reg_w2};
+  const float* rg[3] = {reg_ln_g0, reg_ln_g1, reg_ln_g2};
+  const float* rb[3] = {reg_ln_b0, reg_ln_b1, reg_ln_b2};
+  return dvid::head_tail_launch(fc, cls_w, cls_ln_g, cls_ln_b, logit_w, logit_bias, C, rw, rg, rb, delta_w, delta_bias,
+                                boxes_in, logits_out, boxes_out, M, S(stream));
 }
 
 int dvid_swin_rows(float* x, int write_x, const void* add, int add_mode, const float* gamma, const float* beta,

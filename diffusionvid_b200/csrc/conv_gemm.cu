@@ -9,8 +9,9 @@
 // Tile: 128 output pixels (th x tw patch of one image) x BN output channels, K step 64 channels of one filter tap.
 // The A tile of tap (r,s) is the same 4-D TMA box shifted by (r-pad, s-pad); out-of-bounds rows are zero-filled by
 // TMA, which implements the convolution's zero padding and all tile tails without any predicate in the kernel.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM -> regs -> swizzled smem ->
-// TMA store). Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = TMA store issuer, 4..11 = epilogue (TMEM -> regs
+// -> swizzled smem, two groups alternating 64-column chunks). Two TMEM accumulator stages let the epilogue of tile i
+// overlap the main loop of tile i+1.
 #include <stdlib.h>
 #include "ptx_sm100.cuh"
 #include "dvid_internal.h"
@@ -51,15 +52,23 @@ constexpr int BSTAT_MAX_KB = 4;   // K <= 256
 // named barriers: 1 = the four epilogue warps; FULL/FREE = epilogue warps <-> TMA store warp, per staging buffer
 constexpr int BAR_FULL0 = 2, BAR_FREE0 = 4;
 
-template <int BN, bool BSTAT = false>
+// RES (residual with resid_shift == 0): the residual tile is ADDED BY THE TENSOR CORE.  Each 64-channel chunk of the
+// residual (same 128-pixel patch as the output tile) is TMA-loaded into an A-ring stage like an extra k-block and
+// multiplied by a 16x16 identity held in smem: D[:, 64j+16k .. +16] += R_j[:, 16k .. +16] * I (four N=16 MMAs per
+// chunk, fp16 x 1.0 accumulated in fp32 = exact).  The first version added it in the epilogue from per-thread strided
+// 16-byte global loads, which cost 3-4 us per 64-column chunk (device trace: profiles/r01_trace_res4_conv3.txt).
+constexpr int IDENT_BYTES = 16 * 128;   // 16 rows (n) x 64 k fp16, 128-byte swizzle; I[n][k] = (n == k), k < 16
+
+template <int BN, bool BSTAT = false, bool RES = false>
 struct ConvGemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGES = BSTAT ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8));
+  static constexpr int STAGES0 = BSTAT ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8));
+  static constexpr int STAGES = STAGES0 - (RES ? 1 : 0);   // room for the identity tile (and keeps BN=256 under 227 KB)
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int RING_BYTES =
       BSTAT ? (STAGES * A_STAGE_BYTES + BSTAT_MAX_KB * B_STAGE_BYTES) : (STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
-  static constexpr int SMEM_BYTES =
-      RING_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BN * 4 /*bias staging*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                                    BN * 4 /*bias staging*/ + (RES ? IDENT_BYTES : 0);
 };
 
 // debug event log (DVID_TRACE=1): role r appends (code, clock) pairs to its own 1024-entry lane of p.trace, CTA 0 only
@@ -72,11 +81,12 @@ __device__ __forceinline__ void trace_ev(const ConvGemmParams& p, int role, int&
   }
 }
 
-template <int BN, bool BSTAT>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, bool BSTAT, bool RES>
+__global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BN, BSTAT>;
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                 const ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BN, BSTAT, RES>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (128-byte swizzle atoms) with pointer arithmetic on the __shared__ symbol, so the compiler keeps
@@ -85,14 +95,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * A_STAGE_BYTES;      // ring (normal) or the resident [kb][BN x 64] weight tile (BSTAT)
   uint8_t* sOut = smem + Cfg::RING_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + 2 * OUT_STAGE_BYTES);
+  uint8_t* sIdent = sOut + 2 * OUT_STAGE_BYTES;   // RES: 16x16 identity B tile (1024-byte aligned for the 128B swizzle)
+  uint8_t* sCtl = sIdent + (RES ? IDENT_BYTES : 0);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sCtl);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* bres_full = tmem_empty + 2;           // BSTAT: resident weights landed / may be overwritten
   uint64_t* bres_empty = bres_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_empty + 1);
-  float* sBias = reinterpret_cast<float*>(sOut + 2 * OUT_STAGE_BYTES + 256);   // [BN] bias of the current tile
+  float* sBias = reinterpret_cast<float*>(sCtl + 256);   // [BN] bias of the current tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,13 +121,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
     }
     mbar_init(bres_full, 1);
     mbar_init(bres_empty, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (RES && warp >= 4) {
+    // identity B tile: row n (16 rows of 128 B), element k at 16-byte chunk (k / 8) ^ (n & 7)
+    const int t = threadIdx.x - 128;
+    if (t < IDENT_BYTES / 16) {
+      const int n = t >> 3, chunk = t & 7;        // logical chunk = 8 k-elements
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (chunk == (n >> 3)) {                     // k == n lies in logical chunk n / 8, element n % 8
+        uint32_t w[4] = {0, 0, 0, 0};
+        w[(n & 7) >> 1] = (n & 1) ? 0x3C000000u : 0x00003C00u;   // fp16 1.0 in the low / high half
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      *reinterpret_cast<uint4*>(sIdent + n * 128 + ((chunk ^ (n & 7)) << 4)) = v;
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,6 +214,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         n_idx * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (RES) {
+          const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
+          for (int c = 0; c < nchunks; ++c) {      // residual chunks ride the A ring like extra k-blocks
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES);
+            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmR, &full_bar[stage], n_idx * BN + c * 64, tx * tw, ty * p.th,
+                        img);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -233,12 +270,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           umma_commit(&empty_bar[stage]);
           if (kb == kb_end - 1) {
-            umma_commit(&tmem_full[as]);
+            if (!RES) umma_commit(&tmem_full[as]);
             if (last_of_n) umma_commit(bres_empty);
           }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (RES) {
+        constexpr uint32_t idesc16 = umma_idesc_f16(BLOCK_M, 16);
+        const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t rdesc = umma_desc_sw128_kmajor(smem_u32(sA + stage * A_STAGE_BYTES));
+            const uint64_t idesc_b = umma_desc_sw128_kmajor(smem_u32(sIdent));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem + c * 64 + k * 16, rdesc + 2 * k, idesc_b, idesc16, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (c == nchunks - 1) umma_commit(&tmem_full[as]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -246,7 +301,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================== TMA store warp =====================
     // Takes the staged 128x64 fp16 chunks from the epilogue warps (named barriers FULL0/1) and issues the TMA stores, so
     // the store issue + the wait for the staging buffer to drain are off the epilogue's critical path.
-    if (p.out_f32 == nullptr && !(p.dbg & 16)) {
+    if (p.out_f32 == nullptr && !(p.dbg & 128)) {
       int total_chunks = 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int n_idx, m_idx, split;
@@ -283,23 +338,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Global-memory latency is kept off the per-chunk critical path: the bias of the NEXT tile is fetched into
     // registers while the current tile is processed (and staged through smem), the residual of chunk c+1 is fetched
     // while chunk c is converted.
-    const int ew = warp - 4;  // == warp % 4: the TMEM sub-partition this warp may read
+    // 8 warps = two groups of four; group g converts the 64-column chunks with (global chunk index & 1) == g into
+    // staging buffer g.  Two warps per SM sub-partition hide each other's TMEM-load / smem / barrier latencies (the
+    // 4-warp epilogue sat at ~0.15 IPC and, not the tensor pipe, bounded every K <= 512 layer).  The bias of the NEXT
+    // tile is fetched while the current tile is processed; the residual of a group's next chunk while its current one
+    // is converted.
+    const int ew = (warp - 4) & 3;   // == warp % 4: the TMEM sub-partition this warp may read
+    const int grp = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
-    const int et = threadIdx.x - 128;
-    int staged = 0;
+    const int et = threadIdx.x - 128;          // 0..255
+    int gbase = 0;                             // 64-column chunks staged by both groups before this tile
     int as = 0;
     uint32_t aphase = 0;
     int tn = 0;
-    float bnext[BN / 128 > 0 ? BN / 128 : 1];
+    float bnext = 0.f;
     auto fetch_bias = [&](int tile) {
       int bn_idx, bm_idx, bsplit;
       decode(tile, bn_idx, bm_idx, bsplit);
-      const int n0 = bn_idx * BN;
-#pragma unroll
-      for (int i = 0; i < (BN + 127) / 128; ++i) {
-        const int col = n0 + et + i * 128;
-        bnext[i] = (p.bias != nullptr && (BN >= 128 || et < BN) && col < p.cout) ? __ldg(p.bias + col) : 0.f;
-      }
+      const int col = bn_idx * BN + et;
+      bnext = (p.bias != nullptr && et < BN && col < p.cout) ? __ldg(p.bias + col) : 0.f;
     };
     if (tile_begin < tile_end && p.out_f32 == nullptr) fetch_bias(tile_begin);
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
@@ -313,9 +370,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int y = y0 + (row >> p.tw_log2);
       const bool valid = (x < p.w_out) && (y < p.h_out);
       const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
+      const int c_first = (gbase + grp) & 1;   // first chunk of this tile that belongs to this group
 
       const __half* rrow = nullptr;   // this thread's residual row (channel 0)
-      if (p.resid != nullptr && valid) {
+      if (!RES && p.resid != nullptr && valid) {
         rrow = p.resid + ((static_cast<long long>(img) * p.resid_h + (y >> p.resid_shift)) * p.resid_w +
                           (x >> p.resid_shift)) * p.cout;
       }
@@ -329,18 +387,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          : make_uint4(0, 0, 0, 0);
         }
       };
-      if (p.resid != nullptr) fetch_resid(0);
+      if (!RES && p.resid != nullptr && c_first < nchunks) fetch_resid(c_first);
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       if (et == 0) trace_ev(p, 2, tn, (tile << 8) | 0xfe);       // accumulator ready
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
 
-      if (p.out_f32 != nullptr) {
-        // split-K partials: fp32, direct vector stores (GEMM view: th == 1, row index = x)
+      if (p.dbg & 128) {
+        // experiment: no epilogue work at all (mainloop speed)
+      } else if (p.out_f32 != nullptr) {
+        // split-K partials: fp32, direct vector stores (GEMM view: th == 1, row index = x); 32-column pieces
+        // alternate between the two groups
         float* dst = p.out_f32 + (static_cast<long long>(split) * p.m_total + x) * p.cout;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = grp; c < BN / 32; c += 2) {
           const int ch0 = n_idx * BN + c * 32;
           if (ch0 >= p.cout) break;
           uint32_t v[32];
@@ -358,50 +419,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
-        // stage this tile's bias: the barrier below orders the previous tile's last sBias reads before these writes and
-        // these writes before this tile's reads.  Then start fetching the next tile's bias.
-        if (!(p.dbg & 64)) {
-          named_bar_sync(1, 128);
-#pragma unroll
-          for (int i = 0; i < (BN + 127) / 128; ++i)
-            if (BN >= 128 || et < BN) sBias[et + i * 128] = bnext[i];
-          if (tile + tile_step < tile_end) fetch_bias(tile + tile_step);
-          named_bar_sync(1, 128);
-        }
+        // stage this tile's bias: the first barrier orders the previous tile's last sBias reads before these writes,
+        // the second these writes before this tile's reads.  Then start fetching the next tile's bias.
+        named_bar_sync(1, 256);
+        if (et < BN) sBias[et] = bnext;
+        if (tile + tile_step < tile_end) fetch_bias(tile + tile_step);
+        named_bar_sync(1, 256);
+        uint8_t* buf = sOut + grp * OUT_STAGE_BYTES;
 #pragma unroll 1
-        for (int c = 0; c < nchunks; ++c) {
-          const int sb = staged & 1;
-          uint8_t* buf = sOut + sb * OUT_STAGE_BYTES;
+        for (int c = c_first; c < nchunks; c += 2) {
           uint4 rcur[8];
-          if (p.resid != nullptr) {
+          if (!RES && p.resid != nullptr) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
-            if (c + 1 < nchunks) fetch_resid(c + 1);
+            if (c + 2 < nchunks) fetch_resid(c + 2);
           }
           uint32_t v[2][32];
-          if (!(p.dbg & 2)) {
-            tmem_ld32(tbase + c * 64, v[0]);
-            tmem_ld32(tbase + c * 64 + 32, v[1]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[0][j] = v[1][j] = 0u;
-          }
-          // the store warp has drained the TMA store that last read this staging buffer (two chunks ago)
-          if (staged >= 2 && !(p.dbg & 16)) named_bar_sync(BAR_FREE0 + sb, 160);
-          if (!(p.dbg & 2)) tmem_ld_wait();
+          tmem_ld32(tbase + c * 64, v[0]);
+          tmem_ld32(tbase + c * 64 + 32, v[1]);
+          // the store warp has drained the TMA store that last read this group's staging buffer
+          if (gbase + c >= 2) named_bar_sync(BAR_FREE0 + grp, 160);
+          tmem_ld_wait();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = (p.dbg & 8) ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                            : *reinterpret_cast<const float4*>(sBias + c * 64 + h * 32 + j);
+              const float4 b4 = *reinterpret_cast<const float4*>(sBias + c * 64 + h * 32 + j);
               f[j] = __uint_as_float(v[h][j]) + b4.x;
               f[j + 1] = __uint_as_float(v[h][j + 1]) + b4.y;
               f[j + 2] = __uint_as_float(v[h][j + 2]) + b4.z;
               f[j + 3] = __uint_as_float(v[h][j + 3]) + b4.w;
             }
-            if (p.resid != nullptr) {
+            if (!RES && p.resid != nullptr) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const __half2* rh = reinterpret_cast<const __half2*>(&rcur[h * 4 + q]);
@@ -413,36 +463,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
             }
-            if (p.relu == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            } else if (p.relu == 2) {   // GELU (erf form, torch.nn.GELU default) - Swin MLP, swintransformer.py:47-66
+            if (p.relu == 2) {   // GELU (erf form, torch.nn.GELU default) - Swin MLP, swintransformer.py:47-66
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
             }
-            if (p.dbg & 4) {     // experiment: no conversion / staging (keep the values alive)
-              float acc = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) acc += f[j];
-              if (acc == 123.456f) buf[row] = 1;
-              continue;
-            }
+            const __half2 zero2 = __float2half2_rn(0.f);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 pk;
-              pk.x = pack_half2(f[q * 8 + 0], f[q * 8 + 1]);
-              pk.y = pack_half2(f[q * 8 + 2], f[q * 8 + 3]);
-              pk.z = pack_half2(f[q * 8 + 4], f[q * 8 + 5]);
-              pk.w = pack_half2(f[q * 8 + 6], f[q * 8 + 7]);
+              __half2 h2[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h2[e] = __floats2half2_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
+                if (p.relu == 1) h2[e] = __hmax2(h2[e], zero2);   // ReLU commutes with the rounding to fp16
+              }
               const int chunk = h * 4 + q;  // 16-byte chunk inside the 128-byte row
-              *reinterpret_cast<uint4*>(buf + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
+              *reinterpret_cast<uint4*>(buf + row * 128 + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<uint4*>(h2);
             }
           }
-          if (!(p.dbg & 32)) fence_proxy_async_smem();
-          if (!(p.dbg & 16)) named_bar_arrive(BAR_FULL0 + sb, 160);   // hand the staged chunk to the store warp
+          fence_proxy_async_smem();
+          named_bar_arrive(BAR_FULL0 + grp, 160);   // hand the staged chunk to the store warp, do not wait for it
           if (et == 0) trace_ev(p, 2, tn, (tile << 8) | c);
-          ++staged;
         }
+        gbase += nchunks;
       }
       tc_fence_before();
       __syncwarp();
@@ -517,13 +559,13 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool BSTAT>
-static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p,
-                      cudaStream_t stream) {
-  using Cfg = ConvGemmCfg<BN, BSTAT>;
+template <int BN, bool BSTAT, bool RES>
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                      const ConvGemmParams& p, cudaStream_t stream) {
+  using Cfg = ConvGemmCfg<BN, BSTAT, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, BSTAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, BSTAT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return DVID_ERR_CUDA;
     attr_set = true;
@@ -535,7 +577,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     const size_t bytes = 3 * 2048 * sizeof(unsigned long long);
     cudaMalloc(&q.trace, bytes);
     cudaMemsetAsync(q.trace, 0, bytes, stream);
-    conv_gemm_kernel<BN, BSTAT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, q);
+    conv_gemm_kernel<BN, BSTAT, RES><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, q);
     cudaStreamSynchronize(stream);
     static unsigned long long host[3 * 2048];
     cudaMemcpy(host, q.trace, bytes, cudaMemcpyDeviceToHost);
@@ -553,7 +595,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
       }
     return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
   }
-  conv_gemm_kernel<BN, BSTAT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  conv_gemm_kernel<BN, BSTAT, RES><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
   return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
 }
 
@@ -659,13 +701,32 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   if (bstat_env < 0) { const char* e = getenv("DVID_BSTAT"); bstat_env = e ? atoi(e) : 1; }
   const bool bstat = bstat_env && out_f32 == nullptr && p.total_kb <= BSTAT_MAX_KB && bn >= 128 &&
                      static_cast<long long>(p.m_tiles) * p.n_tiles >= 2LL * num_sms();
-  if (bstat) {
-    if (bn == 256) return launch_cfg<256, true>(tmA, tmB, tmC, p, stream);
-    return launch_cfg<128, true>(tmA, tmB, tmC, p, stream);
+  // residual through the tensor core (identity MMA) whenever it is a same-resolution tensor and the tile is >= 128 wide
+  const bool res_mma = resid != nullptr && resid_shift == 0 && out != nullptr && bn >= 128;
+  CUtensorMap tmR = tmC;
+  if (res_mma) {
+    const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)p.w_out, (uint64_t)p.h_out, (uint64_t)n};
+    const uint64_t strides[3] = {(uint64_t)cout * 2, (uint64_t)p.w_out * cout * 2,
+                                 (uint64_t)p.h_out * p.w_out * cout * 2};
+    const uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)p.th, 1};
+    int r = make_tmap_f16(&tmR, resid, 4, dims, strides, box, nullptr);
+    if (r) return r;
   }
-  if (bn == 256) return launch_cfg<256, false>(tmA, tmB, tmC, p, stream);
-  if (bn == 128) return launch_cfg<128, false>(tmA, tmB, tmC, p, stream);
-  return launch_cfg<64, false>(tmA, tmB, tmC, p, stream);
+  if (bstat) {
+    if (res_mma) {
+      if (bn == 256) return launch_cfg<256, true, true>(tmA, tmB, tmC, tmR, p, stream);
+      return launch_cfg<128, true, true>(tmA, tmB, tmC, tmR, p, stream);
+    }
+    if (bn == 256) return launch_cfg<256, true, false>(tmA, tmB, tmC, tmR, p, stream);
+    return launch_cfg<128, true, false>(tmA, tmB, tmC, tmR, p, stream);
+  }
+  if (res_mma) {
+    if (bn == 256) return launch_cfg<256, false, true>(tmA, tmB, tmC, tmR, p, stream);
+    return launch_cfg<128, false, true>(tmA, tmB, tmC, tmR, p, stream);
+  }
+  if (bn == 256) return launch_cfg<256, false, false>(tmA, tmB, tmC, tmR, p, stream);
+  if (bn == 128) return launch_cfg<128, false, false>(tmA, tmB, tmC, tmR, p, stream);
+  return launch_cfg<64, false, false>(tmA, tmB, tmC, tmR, p, stream);
 }
 
 // Stem convolution 7x7 / stride 2 / pad 3 with 3 input channels (detectron2 BasicStem) as an implicit

@@ -69,6 +69,11 @@ int nms_launch(const float* boxes, const float* scores, const int* labels, const
 int cdist_launch(const float* x, float* out, int n, int d, cudaStream_t stream);
 int fps_launch(int b, int n, int m, const float* dist, float* temp, int* idx, cudaStream_t stream);
 
+int head_tail_launch(const void* fc, const void* cls_w, const float* cls_g, const float* cls_b, const void* logit_w,
+                     const float* logit_bias, int C, const void* const* reg_w, const float* const* reg_g,
+                     const float* const* reg_b, const void* delta_w, const float* delta_bias, const float* boxes_in,
+                     float* logits_out, float* boxes_out, int M, cudaStream_t stream);
+
 int swin_rows_launch(float* X, int write_x, const void* add, int add_mode, const float* gamma, const float* beta,
                      void* out16, float* out32, int out_mode, int B, int H, int W, int C, int shift,
                      cudaStream_t stream);

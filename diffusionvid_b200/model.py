@@ -103,6 +103,7 @@ class DiffusionDet(nn.Module):
         self.use_streams = bool(hp.get("use_streams", True))
         self.frames_per_stream = int(hp.get("frames_per_stream", 4))
         self.debug_trace = False
+        self.fused_tail = bool(hp.get("fused_tail", True))
         self._graphs = {}
         self._streams = []
         self._shard = None
@@ -185,8 +186,8 @@ class DiffusionDet(nn.Module):
                         for i in range(hp["num_reg"])]
             C = hp["num_classes"]
             cpad = (C + 7) // 8 * 8
-            cw = torch.zeros(cpad, 256, device=dev); cw[:C] = sd[pre + "class_logits.weight"]
-            bw = torch.zeros(8, 256, device=dev); bw[:4] = sd[pre + "bboxes_delta.weight"]
+            cw = torch.zeros(max(cpad, 32), 256, device=dev); cw[:C] = sd[pre + "class_logits.weight"]
+            bw = torch.zeros(16, 256, device=dev); bw[:4] = sd[pre + "bboxes_delta.weight"]
             e["cl_w"] = cw.to(H).contiguous(); e["cl_b"] = sd[pre + "class_logits.bias"].contiguous()
             e["bd_w"] = bw.to(H).contiguous(); e["bd_b"] = sd[pre + "bboxes_delta.bias"].contiguous()
             e["ss"] = {}      # time -> modulation vector(s), filled lazily (weights are frozen)
@@ -393,6 +394,11 @@ class DiffusionDet(nn.Module):
                          out_f16=obj16, mod_scale=ss, mod_shift=ss[:, 256:], rows_per_group=M, scale_stride=512,
                          shift_stride=512, out_mod_f16=fc16)
         # towers + predictors
+        C = self.num_classes
+        if self.fused_tail and len(e["cls"]) == 1 and len(e["reg"]) == 3 and C <= 32:
+            logits, nb = ops.head_tail(fc16, e["cls"][0], e["reg"], e["cl_w"], e["cl_b"], C, e["bd_w"], e["bd_b"],
+                                       boxes.view(M, 4))
+            return logits.view(B, N, C), nb.view(B, N, 4), obj32, obj16
         cls = fc16
         for w, lnw in e["cls"]:
             part, s = ops.gemm_partials(cls, w, 1)

@@ -21,8 +21,9 @@ class _prof:
     """Context manager: when ops.PROFILE is a dict, bracket one launch with CUDA events on the launching stream and
     account its algorithmic FLOPs / bytes under `family` (bench.py's live per-kernel roofline measurement)."""
 
-    def __init__(self, family, flops=0.0, nbytes=0.0):
+    def __init__(self, family, flops=0.0, nbytes=0.0, tag=None):
         self.family, self.flops, self.nbytes = family, flops, nbytes
+        self.tag = tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -38,6 +39,11 @@ class _prof:
             rec[0].append((self.s, self.e))
             rec[1] += self.flops
             rec[2] += self.nbytes
+            if self.tag is not None:      # per-shape breakdown (tools/profile_shapes.py)
+                rec = PROFILE.setdefault(self.family + ":" + self.tag, [[], 0.0, 0.0])
+                rec[0].append((self.s, self.e))
+                rec[1] += self.flops
+                rec[2] += self.nbytes
         return False
 
 
@@ -70,7 +76,8 @@ def conv2d(x, w, bias, cout, R, S, stride, pad, relu, resid=None, resid_shift=0,
     if out is None:
         out = torch.empty((n, ho, wo, cout), device=x.device, dtype=H)
     with _prof("conv_gemm", 2.0 * n * ho * wo * cout * R * S * cin,
-               2.0 * (x.numel() + w.numel() + n * ho * wo * cout * (2 if resid is not None else 1))):
+               2.0 * (x.numel() + w.numel() + n * ho * wo * cout * (2 if resid is not None else 1)),
+               tag="conv %dx%d s%d %d->%d @%dx%dx%d%s" % (R, S, stride, cin, cout, n, ho, wo, "+res" if resid is not None else "")):
         check(_lib.lib().dvid_conv2d_nhwc_f16(ptr(x), ptr(w), ptr(bias), ptr(resid), ptr(out), n, h, wd, cin, cout, R,
                                               S, stride, pad, resid_shift, int(relu), cur_stream()),
               "dvid_conv2d_nhwc_f16")
@@ -96,7 +103,7 @@ def gemm(a, w, bias=None, relu=False, resid=None, out=None):
     n = w.shape[0]
     if out is None:
         out = torch.empty((m, n), device=a.device, dtype=H)
-    with _prof("conv_gemm", 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n)):
+    with _prof("conv_gemm", 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n), tag="gemm %dx%d->%d" % (m, k, n)):
         check(_lib.lib().dvid_gemm_f16(ptr(a), ptr(w), ptr(bias), ptr(resid), ptr(out), None, m, n, k, int(relu), 1,
                                        None, cur_stream()), "dvid_gemm_f16")
     _cnt()
@@ -111,7 +118,8 @@ def gemm_partials(a, w, splits=1, out=None):
     if out is None:
         out = torch.empty((max(1, splits), m, n), device=a.device, dtype=F32)
     used = ctypes.c_int(0)
-    with _prof("conv_gemm", 2.0 * m * n * k, 2.0 * (m * k + n * k) + 4.0 * m * n * max(1, splits)):
+    with _prof("conv_gemm", 2.0 * m * n * k, 2.0 * (m * k + n * k) + 4.0 * m * n * max(1, splits),
+               tag="gemm(f32 partials x%d) %dx%d->%d" % (splits, m, k, n)):
         check(_lib.lib().dvid_gemm_f16(ptr(a), ptr(w), None, None, None, ptr(out), m, n, k, 0, splits,
                                        ctypes.byref(used), cur_stream()), "dvid_gemm_f16(partials)")
     _cnt()
@@ -247,6 +255,25 @@ def head_final(logit_part, cls_bias, C, delta_part, delta_bias, boxes_in, logits
                                      ptr(boxes_out), M, cur_stream()), "dvid_head_final")
     _cnt()
     return logits_out, boxes_out
+
+
+def head_tail(fc16, cls, reg, logit_w, logit_b, C, delta_w, delta_b, boxes_in):
+    """Fused cls / reg towers + predictors + apply_deltas (dvid_head_tail).  cls = (w, (g, b)); reg = 3 x (w, (g, b));
+    logit_w [32][256], delta_w [16][256] fp16 zero-padded.  Returns (logits [M,C], boxes [M,4]) fp32."""
+    _chk(fc16, H, "fc16"); _chk(boxes_in, F32, "boxes_in"); _chk(logit_w, H, "logit_w"); _chk(delta_w, H, "delta_w")
+    M = fc16.shape[0]
+    dev = fc16.device
+    logits = torch.empty((M, C), device=dev, dtype=F32)
+    boxes = torch.empty((M, 4), device=dev, dtype=F32)
+    (cw, (cg, cb)) = cls
+    with _prof("head_tail", 2.0 * M * 256 * (4 * 256 + 34), 2.0 * M * 256 + 4.0 * M * (C + 8)):
+        check(_lib.lib().dvid_head_tail(ptr(fc16), ptr(cw), ptr(cg), ptr(cb), ptr(logit_w), ptr(logit_b), C,
+                                        ptr(reg[0][0]), ptr(reg[1][0]), ptr(reg[2][0]),
+                                        ptr(reg[0][1][0]), ptr(reg[0][1][1]), ptr(reg[1][1][0]), ptr(reg[1][1][1]),
+                                        ptr(reg[2][1][0]), ptr(reg[2][1][1]), ptr(delta_w), ptr(delta_b),
+                                        ptr(boxes_in), ptr(logits), ptr(boxes), M, cur_stream()), "dvid_head_tail")
+    _cnt()
+    return logits, boxes
 
 
 # ------------------------------------------------------------------------------------------------ diffusion loop

@@ -127,6 +127,19 @@ DVID_API int dvid_head_final(const float* logit_part, int ldl, const float* cls_
                     const float* delta_bias, const float* boxes_in, float* logits_out, float* boxes_out, int M,
                     void* stream);
 
+/* Fused tail of RCNNHead.forward / RCNNHead_cond.forward (box_head.py:538-548, :649-664) for NUM_CLS = 1, NUM_REG = 3:
+ * cls tower (Linear no-bias + LayerNorm + ReLU) -> class_logits (+bias); reg tower x3 -> bboxes_delta (+bias) ->
+ * apply_deltas (:550-590).  One CTA per 128 rows keeps the activations in shared memory across the six tcgen05 GEMMs.
+ * fc [M][256] fp16 (time/cond-modulated object features); cls_w / reg_w* [256][256] fp16; logit_w [32][256] fp16 (rows
+ * >= C zero); delta_w [16][256] fp16 (rows >= 4 zero); LayerNorm params and biases fp32; boxes_in [M][4] xyxy;
+ * logits_out [M][C], boxes_out [M][4] fp32. */
+DVID_API int dvid_head_tail(const void* fc, const void* cls_w, const float* cls_ln_g, const float* cls_ln_b,
+                   const void* logit_w, const float* logit_bias, int C, const void* reg_w0, const void* reg_w1,
+                   const void* reg_w2, const float* reg_ln_g0, const float* reg_ln_b0, const float* reg_ln_g1,
+                   const float* reg_ln_b1, const float* reg_ln_g2, const float* reg_ln_b2, const void* delta_w,
+                   const float* delta_bias, const float* boxes_in, float* logits_out, float* boxes_out, int M,
+                   void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Diffusion loop, csrc/rowops.cu + csrc/postproc.cu.
  */

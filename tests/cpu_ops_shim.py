@@ -163,6 +163,19 @@ def time_sinusoid(t, freq):
     return torch.cat((e.sin(), e.cos()), dim=-1)
 
 
+def head_tail(fc16, cls, reg, logit_w, logit_b, C, delta_w, delta_b, boxes_in):
+    def tower(x, w, ln):
+        y = F.linear(x.float(), w.float())
+        return F.relu(F.layer_norm(y, (256,), ln[0], ln[1], 1e-5)).half()
+    c = tower(fc16, cls[0], cls[1])
+    logits = F.linear(c.float(), logit_w.float()[:C], logit_b)
+    r = fc16
+    for w, ln in reg:
+        r = tower(r, w, ln)
+    deltas = F.linear(r.float(), delta_w.float()[:4], delta_b)
+    return logits, om.apply_deltas(deltas, boxes_in)
+
+
 def head_final(logit_part, cls_bias, C, delta_part, delta_bias, boxes_in, logits_out=None, boxes_out=None):
     return logit_part[:, :C] + cls_bias, om.apply_deltas(delta_part[:, :4] + delta_bias, boxes_in)
 

@@ -369,3 +369,39 @@ def test_preprocess_maxpool_stem(cuda):
     p = ops.maxpool3x3s2(y)
     pref = F.max_pool2d(y.float().cpu().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
     assert torch.equal(p.float().cpu(), pref)
+
+
+@pytest.mark.parametrize("M", [100, 2400])
+def test_fused_head_tail_matches_layerwise_math(cuda, M):
+    """dvid_head_tail (cls tower -> logits, 3 x reg tower -> deltas -> apply_deltas, box_head.py:538-590) vs the same
+    chain in torch with fp16 rounding of the inter-layer activations; ragged last tile (M % 128 != 0)."""
+    import torch.nn.functional as F
+    from oracle import model as om
+    g = torch.Generator().manual_seed(M)
+    C = 30
+    fc = torch.randn(M, 256, generator=g).half()
+    mk = lambda n: (torch.randn(n, 256, generator=g) / 16).half()
+    ln = lambda: (1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g))
+    cls = (mk(256), ln())
+    reg = [(mk(256), ln()) for _ in range(3)]
+    lw = torch.zeros(32, 256).half(); lw[:C] = mk(C)
+    dw = torch.zeros(16, 256).half(); dw[:4] = mk(4) * 0.25
+    lb, db = 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(4, generator=g)
+    xy = torch.rand(M, 2, generator=g) * 300
+    boxes = torch.cat([xy, xy + torch.rand(M, 2, generator=g) * 200 + 1], 1)
+    dev = lambda t: t.to(cuda)
+    lg, bx = ops.head_tail(dev(fc), (dev(cls[0]), (dev(cls[1][0]), dev(cls[1][1]))),
+                           [(dev(w), (dev(a), dev(b))) for w, (a, b) in reg], dev(lw), dev(lb), C, dev(dw), dev(db),
+                           dev(boxes))
+
+    def tower(x, w, p):
+        return F.relu(F.layer_norm(F.linear(x.float(), w.float()), (256,), p[0], p[1], 1e-5)).half()
+    c = tower(fc, *cls)
+    ref_lg = F.linear(c.float(), lw.float()[:C], lb)
+    r = fc
+    for w, p in reg:
+        r = tower(r, w, p)
+    ref_bx = om.apply_deltas(F.linear(r.float(), dw.float()[:4], db), boxes)
+    assert lg.shape == (M, C) and bx.shape == (M, 4)
+    assert (lg.cpu() - ref_lg).abs().max().item() <= 5e-3
+    assert (bx.cpu() - ref_bx).abs().max().item() <= 5e-3 * 500
