@@ -40,7 +40,7 @@ SIGNATURES = {
     "dvid_topk_scores": [P, P, I, I, I, I, P, P, P, I, I, P],
     "dvid_topk_mask": [P, I, I, I, I, I, P, P, P],
     "dvid_gather_masked_rows": [P, P, I, I, I, P, P],
-    "dvid_nms": [P, P, P, P, I, I, I, F, I, I, I, F, F, P, P, P, P, P, P],
+    "dvid_nms": [P, P, P, P, I, I, I, F, I, I, I, F, F, P, P, P, P, P, P, L, P],
     "dvid_cdist_f32": [P, P, I, I, P],
     "dvid_furthest_point_sampling": [I, I, I, P, P, P, P],
     "dvid_swin_rows": [P, I, P, I, P, P, P, P, I, I, I, I, I, I, P],

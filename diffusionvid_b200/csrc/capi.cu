@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 4
+#define DVID_ABI_VERSION 5
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -151,10 +151,12 @@ int dvid_gather_masked_rows(const float* src, const unsigned char* mask, int fra
 
 int dvid_nms(const float* boxes, const float* scores, const int* labels, const int* counts, int n, int cap,
              int frames, float thr, int plus_one, int ge, int ascending_out, float clip_w, float clip_h,
-             long long* keep_idx, float* out_boxes, float* out_scores, int* out_labels, int* out_count, void* stream) {
+             long long* keep_idx, float* out_boxes, float* out_scores, int* out_labels, int* out_count,
+             void* workspace, long workspace_bytes, void* stream) {
   if (!boxes || !scores || !out_count) return DVID_ERR_ARG;
   return dvid::nms_launch(boxes, scores, labels, counts, n, cap, frames, thr, plus_one, ge, ascending_out, clip_w,
-                          clip_h, keep_idx, out_boxes, out_scores, out_labels, out_count, S(stream));
+                          clip_h, keep_idx, out_boxes, out_scores, out_labels, out_count, workspace,
+                          workspace_bytes > 0 ? static_cast<size_t>(workspace_bytes) : 0, S(stream));
 }
 
 int dvid_cdist_f32(const float* x, float* out, int n, int d, void* stream) {

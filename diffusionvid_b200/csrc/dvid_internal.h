@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #define DVID_OK 0
@@ -65,7 +66,7 @@ int gather_masked_rows_launch(const float* src, const unsigned char* mask, int f
 int nms_launch(const float* boxes, const float* scores, const int* labels, const int* counts, int n, int cap,
                int frames, float thr, int plus_one, int ge, int ascending_out, float clip_w, float clip_h,
                long long* keep_idx, float* out_boxes, float* out_scores, int* out_labels, int* out_count,
-               cudaStream_t stream);
+               void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int cdist_launch(const float* x, float* out, int n, int d, cudaStream_t stream);
 int fps_launch(int b, int n, int m, const float* dist, float* temp, int* idx, cudaStream_t stream);
 

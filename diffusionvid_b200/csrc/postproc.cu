@@ -36,31 +36,110 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
 // ------------------------------------------------------------------------------------------------ top-k of N*C scores
-// key = score bits (positive floats order like unsigned ints) << 32 | ~flat_index  -> descending sort gives
-// score-descending, flat-index-ascending order (the canonical order of SURVEY.md 8c contract 3).
-__global__ void __launch_bounds__(1024)
-topk_scores_kernel(const float* __restrict__ logits, const float* __restrict__ boxes, int N, int C, int k, int n_pad,
-                   float* __restrict__ out_boxes, float* __restrict__ out_scores, int* __restrict__ out_labels,
-                   int cap, int slot0) {
-  extern __shared__ __align__(16) unsigned long long skeys[];
-  const int f = blockIdx.x;
-  const int total = N * C;
-  const float* lg = logits + static_cast<long>(f) * total;
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-    unsigned long long key = 0ull;
-    if (i < total) {
-      const float s = sigmoidf_ref(lg[i]);
-      key = (static_cast<unsigned long long>(__float_as_uint(s)) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(i));
+// Exclusive prefix sum of one int per thread over the CTA (1024 threads); returns the prefix, *total = CTA sum.
+__device__ __forceinline__ int block_excl_scan(int v, int* swarp, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) swarp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = swarp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
     }
-    skeys[i] = key;
+    swarp[lane] = w;      // inclusive over warps
   }
   __syncthreads();
-  bitonic_sort_desc(skeys, n_pad);
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const unsigned long long key = skeys[i];
+  const int base = warp ? swarp[warp - 1] : 0;
+  *total = swarp[31];
+  __syncthreads();        // swarp may be reused by the caller
+  return base + inc - v;
+}
+
+// Per frame: radix-select the k-th largest score (4 x 8-bit passes over the fp32 bit patterns - sigmoid outputs are
+// positive, so they order like unsigned ints), compact the k winners in flat-index order (ties at the threshold are
+// resolved towards the lowest flat index) and bitonic-sort just those <= 1024 keys.
+// key = score bits << 32 | ~flat_index -> descending sort gives score-descending, flat-index-ascending order (the
+// canonical order of SURVEY.md 8c contract 3).  The first version sorted all 16384 padded keys (255 us per call).
+__global__ void __launch_bounds__(1024)
+topk_scores_kernel(const float* __restrict__ logits, const float* __restrict__ boxes, int N, int C, int k,
+                   float* __restrict__ out_boxes, float* __restrict__ out_scores, int* __restrict__ out_labels,
+                   int cap, int slot0) {
+  extern __shared__ __align__(16) unsigned char tk_smem[];
+  unsigned long long* skeys = reinterpret_cast<unsigned long long*>(tk_smem);        // 1024 selected keys
+  unsigned* su = reinterpret_cast<unsigned*>(tk_smem + 1024 * 8);                      // N*C score bit patterns
+  __shared__ int hist[256];
+  __shared__ int swarp[32];
+  __shared__ unsigned s_prefix;
+  __shared__ int s_remaining;
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int total = N * C;
+  const float* lg = logits + static_cast<long>(f) * total;
+  for (int i = tid; i < total; i += blockDim.x) su[i] = __float_as_uint(sigmoidf_ref(lg[i]));
+  skeys[tid] = 0ull;
+  if (tid == 0) { s_prefix = 0u; s_remaining = k; }
+  __syncthreads();
+  // ---- radix select: after pass p the top (4-p) bytes of the k-th largest value are known
+  for (int pass = 3; pass >= 0; --pass) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned hi_mask = pass == 3 ? 0u : (0xFFFFFFFFu << (8 * (pass + 1)));
+    for (int i = tid; i < total; i += blockDim.x) {
+      const unsigned u = su[i];
+      if ((u & hi_mask) == prefix) atomicAdd(&hist[(u >> (8 * pass)) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rem = s_remaining, b = 255;
+      for (; b > 0; --b) {
+        if (hist[b] >= rem) break;
+        rem -= hist[b];
+      }
+      s_prefix = prefix | (static_cast<unsigned>(b) << (8 * pass));
+      s_remaining = rem;     // how many elements of the chosen bin (finally: equal to the threshold) are still needed
+    }
+    __syncthreads();
+  }
+  const unsigned thr = s_prefix;
+  const int need_eq = s_remaining;
+  // ---- ordered compaction: thread t owns the contiguous flat indices [t*per, (t+1)*per)
+  const int per = (total + 1023) / 1024;
+  const int i0 = tid * per, i1 = min(total, i0 + per);
+  int n_gt = 0, n_eq = 0;
+  for (int i = i0; i < i1; ++i) {
+    const unsigned u = su[i];
+    n_gt += (u > thr);
+    n_eq += (u == thr);
+  }
+  int tot_gt, tot_eq;
+  int p_gt = block_excl_scan(n_gt, swarp, &tot_gt);
+  int p_eq = block_excl_scan(n_eq, swarp, &tot_eq);
+  for (int i = i0; i < i1; ++i) {
+    const unsigned u = su[i];
+    int slot = -1;
+    if (u > thr) slot = p_gt++;
+    else if (u == thr) {
+      if (p_eq < need_eq) slot = tot_gt + p_eq;
+      ++p_eq;
+    }
+    if (slot >= 0) skeys[slot] = (static_cast<unsigned long long>(u) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(i));
+  }
+  __syncthreads();
+  bitonic_sort_desc(skeys, 1024);
+  if (tid < k) {
+    const unsigned long long key = skeys[tid];
     const unsigned idx = 0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFull);
     const int box = idx / C, cls = idx % C;
-    const long o = static_cast<long>(f) * cap + slot0 + i;
+    const long o = static_cast<long>(f) * cap + slot0 + tid;
     out_scores[o] = __uint_as_float(static_cast<unsigned>(key >> 32));
     out_labels[o] = cls + 1;
     *reinterpret_cast<float4*>(out_boxes + o * 4) =
@@ -136,6 +215,11 @@ struct NmsArgs {
   long long* keep_idx;   // [frames][cap] int64 or nullptr
   float* out_boxes; float* out_scores; int* out_labels;   // compacted outputs or nullptr
   int* out_count;        // [frames]
+  // multi-kernel path (workspace given): phase 1 = sort, (mask kernel), phase 2 = sweep + outputs; phase 0 = all in one
+  int phase;
+  unsigned long long* ws_keys;   // [frames][1024]
+  float4* ws_boxes;              // [frames][1024] sorted, class-offset boxes
+  unsigned long long* ws_mask;   // [frames][1024][16]
 };
 
 constexpr int NMS_MAX = 1024;
@@ -158,6 +242,17 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs a) {
   const float* scores = a.scores + static_cast<long>(f) * a.cap;
   const int* labels = a.labels ? a.labels + static_cast<long>(f) * a.cap : nullptr;
 
+  const int words = (n + 63) >> 6;
+  const float one = a.plus_one ? 1.0f : 0.0f;
+  if (a.phase == 2) {
+    // sorted keys and the suppression matrix were produced by phase 1 + nms_mask_kernel
+    skeys[tid] = a.ws_keys[static_cast<long>(f) * NMS_MAX + tid];
+    if (tid < NMS_WORDS) { skept[tid] = 0ull; skept2[tid] = 0ull; }
+    const uint4* src = reinterpret_cast<const uint4*>(a.ws_mask + static_cast<long>(f) * NMS_MAX * NMS_WORDS);
+    uint4* dst = reinterpret_cast<uint4*>(smask);
+    for (int i = tid; i < n * NMS_WORDS / 2; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  } else {
   // max coordinate (torchvision batched_nms: offsets = idxs * (boxes.max() + 1))
   float mx = -INFINITY;
   float4 mybox = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -194,42 +289,67 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs a) {
   }
   __syncthreads();
 
-  // suppression bit matrix over sorted positions: bit j of smask[i][w] set iff j > i and IoU(i, j) beats thr
-  const int words = (n + 63) >> 6;
-  const float one = a.plus_one ? 1.0f : 0.0f;
-  for (int p = tid; p < n * words; p += blockDim.x) {
-    const int i = p / words, w = p - i * words;
+  if (a.phase == 1) {
+    a.ws_keys[static_cast<long>(f) * NMS_MAX + tid] = skeys[tid];
+    a.ws_boxes[static_cast<long>(f) * NMS_MAX + tid] = (tid < n) ? sbox[tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+
+  // suppression bit matrix over sorted positions: bit j of smask[i][w] set iff j > i and IoU(i, j) beats thr.
+  // One warp per row i, lanes over consecutive j (conflict-free sbox reads, bi is a broadcast), 32 bits per ballot.
+  unsigned* smask32 = reinterpret_cast<unsigned*>(smask);
+  for (int i = warp; i < n; i += 32) {
     const float4 bi = sbox[i];
     const float sa = __fmul_rn(__fadd_rn(__fsub_rn(bi.z, bi.x), one), __fadd_rn(__fsub_rn(bi.w, bi.y), one));
-    unsigned long long bits = 0ull;
-    const int j0 = w * 64;
-    for (int jj = 0; jj < 64; ++jj) {
-      const int j = j0 + jj;
-      if (j <= i || j >= n) continue;
-      const float4 bj = sbox[j];
-      const float left = fmaxf(bi.x, bj.x), right = fminf(bi.z, bj.z);
-      const float top = fmaxf(bi.y, bj.y), bottom = fminf(bi.w, bj.w);
-      const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), one), 0.f);
-      const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), one), 0.f);
-      const float inter = __fmul_rn(width, height);
-      const float sb = __fmul_rn(__fadd_rn(__fsub_rn(bj.z, bj.x), one), __fadd_rn(__fsub_rn(bj.w, bj.y), one));
-      const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
-      const bool sup = a.ge ? (iou >= a.thr) : (iou > a.thr);
-      if (sup) bits |= (1ull << jj);
+    for (int h = 0; h < 2 * words; ++h) {          // 32-bit half words
+      const int j = h * 32 + lane;
+      bool sup = false;
+      if (h * 32 + 31 > i && j > i && j < n) {
+        const float4 bj = sbox[j];
+        const float left = fmaxf(bi.x, bj.x), right = fminf(bi.z, bj.z);
+        const float top = fmaxf(bi.y, bj.y), bottom = fminf(bi.w, bj.w);
+        const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), one), 0.f);
+        const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), one), 0.f);
+        const float inter = __fmul_rn(width, height);
+        // disjoint boxes (almost all pairs: other classes sit at other coordinate offsets): IoU = 0 (or 0/0 = NaN),
+        // neither beats a positive threshold - skip the division.  Exact: same outcome as evaluating it.
+        if (inter > 0.f || !(a.thr > 0.f)) {
+          const float sb = __fmul_rn(__fadd_rn(__fsub_rn(bj.z, bj.x), one), __fadd_rn(__fsub_rn(bj.w, bj.y), one));
+          const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
+          sup = a.ge ? (iou >= a.thr) : (iou > a.thr);
+        }
+      }
+      const unsigned bits = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0) smask32[(i * NMS_WORDS) * 2 + h] = bits;      // little-endian halves of the 64-bit word
     }
-    smask[i * NMS_WORDS + w] = bits;
   }
   __syncthreads();
+  }   // phase != 2
 
-  // greedy sweep by warp 0: lane w (< words) owns word w of the removed set
+  // greedy sweep by warp 0, 64 sorted boxes at a time: the chunk's own (diagonal) words resolve the chunk serially
+  // (one dependent smem read per box), then the surviving rows are OR-ed into the removed set, lane w owning word w.
   if (warp == 0) {
     unsigned long long removed = 0ull, kept = 0ull;
-    for (int i = 0; i < n; ++i) {
-      const int w = i >> 6;
-      const unsigned long long rw = __shfl_sync(0xffffffffu, removed, w);
-      if (!((rw >> (i & 63)) & 1ull)) {
-        if (lane == w) kept |= (1ull << (i & 63));
-        if (lane < words) removed |= smask[i * NMS_WORDS + lane];
+    for (int c = 0; c < words; ++c) {
+      unsigned long long cur = __shfl_sync(0xffffffffu, removed, c);
+      unsigned long long kc = 0ull;
+      const int cn = min(64, n - c * 64);
+      for (int bb = 0; bb < cn; ++bb) {
+        if (!((cur >> bb) & 1ull)) {
+          kc |= (1ull << bb);
+          cur |= smask[(c * 64 + bb) * NMS_WORDS + c];
+        }
+      }
+      if (lane == c) kept = kc;
+      if (lane > c && lane < words) {
+        unsigned long long acc = removed;
+        unsigned long long m = kc;
+        while (m) {
+          const int bb = __ffsll(static_cast<long long>(m)) - 1;
+          m &= m - 1;
+          acc |= smask[(c * 64 + bb) * NMS_WORDS + lane];
+        }
+        removed = acc;
       }
     }
     if (lane < NMS_WORDS) skept[lane] = (lane < words) ? kept : 0ull;
@@ -263,6 +383,43 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs a) {
     }
     if (a.out_scores) a.out_scores[o] = scores[orig];
     if (a.out_labels && labels) a.out_labels[o] = labels[orig];
+  }
+}
+
+// Suppression matrix for the multi-kernel NMS path: one warp per sorted row i, grid (ceil(1024/8), frames), so the
+// O(n^2) IoU work of a frame spreads over ~113 CTAs instead of one (the single-CTA version was issue-bound at ~140 us).
+__global__ void __launch_bounds__(256)
+nms_mask_kernel(const float4* __restrict__ ws_boxes, const int* __restrict__ counts, int n_fixed, int cap, float thr,
+                int plus_one, int ge, unsigned long long* __restrict__ ws_mask) {
+  const int f = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n = counts ? min(counts[f], cap) : n_fixed;
+  if (i >= n) return;
+  const int words = (n + 63) >> 6;
+  const float one = plus_one ? 1.0f : 0.0f;
+  const float4* sbox = ws_boxes + static_cast<long>(f) * NMS_MAX;
+  unsigned* m32 = reinterpret_cast<unsigned*>(ws_mask + (static_cast<long>(f) * NMS_MAX + i) * NMS_WORDS);
+  const float4 bi = sbox[i];
+  const float sa = __fmul_rn(__fadd_rn(__fsub_rn(bi.z, bi.x), one), __fadd_rn(__fsub_rn(bi.w, bi.y), one));
+  for (int h = 0; h < 2 * words; ++h) {
+    const int j = h * 32 + lane;
+    bool sup = false;
+    if (h * 32 + 31 > i && j > i && j < n) {
+      const float4 bj = sbox[j];
+      const float left = fmaxf(bi.x, bj.x), right = fminf(bi.z, bj.z);
+      const float top = fmaxf(bi.y, bj.y), bottom = fminf(bi.w, bj.w);
+      const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), one), 0.f);
+      const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), one), 0.f);
+      const float inter = __fmul_rn(width, height);
+      if (inter > 0.f || !(thr > 0.f)) {       // see nms_kernel: skipping the division for disjoint boxes is exact
+        const float sb = __fmul_rn(__fadd_rn(__fsub_rn(bj.z, bj.x), one), __fadd_rn(__fsub_rn(bj.w, bj.y), one));
+        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
+        sup = ge ? (iou >= thr) : (iou > thr);
+      }
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, sup);
+    if (lane == 0) m32[h] = bits;
   }
 }
 
@@ -383,19 +540,18 @@ fps_kernel(int n, int m, int log2_bs, const float* __restrict__ dist, float* __r
 
 int topk_scores_launch(const float* logits, const float* boxes, int frames, int N, int C, int k, float* out_boxes,
                        float* out_scores, int* out_labels, int cap, int slot0, cudaStream_t stream) {
-  if (frames <= 0 || N <= 0 || C <= 0 || k <= 0 || k > N * C || slot0 + k > cap) return DVID_ERR_SHAPE;
-  int n_pad = 1;
-  while (n_pad < N * C) n_pad <<= 1;
-  if (n_pad > 16384) return DVID_ERR_SHAPE;
+  if (frames <= 0 || N <= 0 || C <= 0 || k <= 0 || k > N * C || k > 1024 || slot0 + k > cap) return DVID_ERR_SHAPE;
+  const size_t smem = 1024 * 8 + static_cast<size_t>(N) * C * 4;
+  if (smem > 200 * 1024) return DVID_ERR_SHAPE;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(topk_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8) !=
+    if (cudaFuncSetAttribute(topk_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
         cudaSuccess)
       return DVID_ERR_CUDA;
     attr_set = true;
   }
-  topk_scores_kernel<<<frames, 1024, n_pad * 8, stream>>>(logits, boxes, N, C, k, n_pad, out_boxes, out_scores,
-                                                          out_labels, cap, slot0);
+  topk_scores_kernel<<<frames, 1024, smem, stream>>>(logits, boxes, N, C, k, out_boxes, out_scores, out_labels, cap,
+                                                     slot0);
   return check_launch();
 }
 
@@ -416,7 +572,7 @@ int gather_masked_rows_launch(const float* src, const unsigned char* mask, int f
 int nms_launch(const float* boxes, const float* scores, const int* labels, const int* counts, int n, int cap,
                int frames, float thr, int plus_one, int ge, int ascending_out, float clip_w, float clip_h,
                long long* keep_idx, float* out_boxes, float* out_scores, int* out_labels, int* out_count,
-               cudaStream_t stream) {
+               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (frames <= 0 || cap <= 0 || n < 0 || n > NMS_MAX || n > cap || out_count == nullptr) return DVID_ERR_SHAPE;
   if (counts != nullptr && cap > NMS_MAX) return DVID_ERR_SHAPE;
   const int smem = NMS_MAX * 24 + NMS_MAX * NMS_WORDS * 8;
@@ -431,6 +587,22 @@ int nms_launch(const float* boxes, const float* scores, const int* labels, const
   a.plus_one = plus_one; a.ge = ge; a.ascending_out = ascending_out; a.clip_w = clip_w; a.clip_h = clip_h;
   a.keep_idx = keep_idx; a.out_boxes = out_boxes; a.out_scores = out_scores; a.out_labels = out_labels;
   a.out_count = out_count;
+  a.phase = 0; a.ws_keys = nullptr; a.ws_boxes = nullptr; a.ws_mask = nullptr;
+  const size_t per_frame = NMS_MAX * 8 + NMS_MAX * 16 + static_cast<size_t>(NMS_MAX) * NMS_WORDS * 8;
+  if (workspace != nullptr && workspace_bytes >= per_frame * frames) {
+    // sort -> suppression matrix over many CTAs -> sweep + outputs
+    unsigned char* w = static_cast<unsigned char*>(workspace);
+    a.ws_keys = reinterpret_cast<unsigned long long*>(w);
+    a.ws_boxes = reinterpret_cast<float4*>(w + static_cast<size_t>(frames) * NMS_MAX * 8);
+    a.ws_mask = reinterpret_cast<unsigned long long*>(w + static_cast<size_t>(frames) * NMS_MAX * 24);
+    a.phase = 1;
+    nms_kernel<<<frames, 1024, smem, stream>>>(a);
+    dim3 grid((NMS_MAX + 7) / 8, frames);
+    nms_mask_kernel<<<grid, 256, 0, stream>>>(a.ws_boxes, counts, n, cap, thr, plus_one, ge, a.ws_mask);
+    a.phase = 2;
+    nms_kernel<<<frames, 1024, smem, stream>>>(a);
+    return check_launch();
+  }
   nms_kernel<<<frames, 1024, smem, stream>>>(a);
   return check_launch();
 }

@@ -330,6 +330,9 @@ def gather_masked_rows(src, mask, k):
     return dst
 
 
+NMS_WS_PER_FRAME = 1024 * 8 + 1024 * 16 + 1024 * 16 * 8   # DVID_NMS_WORKSPACE_PER_FRAME
+
+
 def nms(boxes, scores, labels=None, counts=None, n=None, thr=0.5, plus_one=False, ge=False, ascending_out=False,
         clip_wh=None, want_compact=True):
     """boxes [frames][cap][4], scores [frames][cap], labels int32 [frames][cap] or None.
@@ -346,10 +349,12 @@ def nms(boxes, scores, labels=None, counts=None, n=None, thr=0.5, plus_one=False
     os_ = torch.empty((frames, cap), device=dev, dtype=F32) if want_compact else None
     ol = torch.empty((frames, cap), device=dev, dtype=torch.int32) if (want_compact and labels is not None) else None
     cw, ch = clip_wh if clip_wh is not None else (0.0, 0.0)
+    ws_bytes = frames * NMS_WS_PER_FRAME
+    ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
     check(_lib.lib().dvid_nms(ptr(boxes), ptr(scores), ptr(labels), ptr(counts), n, cap, frames, thr, int(plus_one),
                               int(ge), int(ascending_out), cw, ch, ptr(keep), ptr(ob), ptr(os_), ptr(ol), ptr(count),
-                              cur_stream()), "dvid_nms")
-    _cnt()
+                              ptr(ws), ws_bytes, cur_stream()), "dvid_nms")
+    _cnt(3)
     return dict(keep=keep, count=count, boxes=ob, scores=os_, labels=ol)
 
 

@@ -163,10 +163,15 @@ DVID_API int dvid_gather_masked_rows(const float* src, const unsigned char* mask
 /* Greedy NMS, one CTA per frame, n <= 1024 candidates, sweep on the device.  labels != NULL: torchvision batched_nms
  * coordinate trick (diffusion_det.py:617,793).  plus_one/ge/ascending_out select the legacy mega_core._C.nms
  * semantics (mega_core/csrc/cpu/nms_cpu.cpp:5-65, cuda/nms.cu:13-67).  clip_w>0 applies BoxList.clip_to_image
- * (mega_core/structures/bounding_box.py:214-224) to out_boxes.  keep_idx is int64 like the reference's return. */
+ * (mega_core/structures/bounding_box.py:214-224) to out_boxes.  keep_idx is int64 like the reference's return.
+ * workspace (optional, device, >= frames * DVID_NMS_WORKSPACE_PER_FRAME bytes): with it the O(n^2) suppression matrix
+ * is computed by a separate kernel spread over the whole GPU (sort -> matrix -> sweep, three launches); without it
+ * one CTA per frame does everything.  Results are identical. */
+#define DVID_NMS_WORKSPACE_PER_FRAME (1024 * 8 + 1024 * 16 + 1024 * 16 * 8)
 DVID_API int dvid_nms(const float* boxes, const float* scores, const int* labels, const int* counts, int n, int cap,
              int frames, float thr, int plus_one, int ge, int ascending_out, float clip_w, float clip_h,
-             long long* keep_idx, float* out_boxes, float* out_scores, int* out_labels, int* out_count, void* stream);
+             long long* keep_idx, float* out_boxes, float* out_scores, int* out_labels, int* out_count,
+             void* workspace, long workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Global memory management (diffusion_det.py:841-896).

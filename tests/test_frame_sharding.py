@@ -21,6 +21,15 @@ GIDX = [9, 2, 5]
 
 
 def _run(rank, world, T, port, out_dir):
+    real_ops, real_threads = pm.ops, torch.get_num_threads()
+    try:
+        _run_impl(rank, world, T, port, out_dir)
+    finally:            # the world == 1 run happens inside the pytest process: do not leak the shim to other tests
+        pm.ops = real_ops
+        torch.set_num_threads(real_threads)
+
+
+def _run_impl(rank, world, T, port, out_dir):
     torch.set_num_threads(1)       # same CPU kernels in every process: results must not depend on the world size
     pm.ops = cpu_ops_shim
     hp = dict(SMALL, sample_step=T)

@@ -1,0 +1,22 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from diffusionvid_b200 import ops
+dev = torch.device("cuda")
+g = torch.Generator().manual_seed(0)
+B, N, C = 8, 300, 30
+logits = (torch.randn(B, N, C, generator=g) * 2 - 2).to(dev)
+xy = torch.rand(B, N, 2, generator=g) * 700
+boxes = torch.cat([xy, xy + torch.rand(B, N, 2, generator=g) * 300 + 1], -1).to(dev)
+cap = 900
+eb = torch.empty(B, cap, 4, device=dev); es = torch.empty(B, cap, device=dev); el = torch.empty(B, cap, device=dev, dtype=torch.int32)
+def t(fn, reps=20):
+    fn(); torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps): fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) * 1e3 / reps
+print("topk_scores us", t(lambda: [ops.topk_scores(logits, boxes, N, eb, es, el, i * N) for i in range(3)]) / 3)
+print("nms us", t(lambda: ops.nms(eb, es, el, thr=0.5, clip_wh=(1000., 600.))))
+print("topk_mask us", t(lambda: ops.topk_mask(logits, 75, 25)))
