@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--backbone", default="r101", choices=["r101", "swinb"],
                     help="r101: vid_R_101_DiffusionVID.yaml (headline); swinb: vid_Swin_B_DiffusionVID.yaml "
                          "(INFER_BATCH 4, ALL_FRAME_INTERVAL 4)")
+    ap.add_argument("--frames-per-stream", type=int, default=0,
+                    help="frames of a batch per parallel stream branch inside the captured units (0 = model default)")
     ap.add_argument("--shard", default="videos", choices=["videos", "frames"],
                     help="N>1: 'videos' = every rank runs its own clips (reference scheme, weak scaling); 'frames' = "
                          "the frames of ONE clip are dealt to the ranks, one all-gather of memory candidates per "
@@ -257,6 +259,8 @@ def run_ours(args):
     m = pm.DiffusionDet(hp)
     m.load_state_dict(synth.make_state_dict(seed=1234, blocks=hp["blocks"], swin=hp.get("swin")), strict=False)
     m.to(dev)
+    if args.frames_per_stream > 0:
+        m.frames_per_stream = args.frames_per_stream
     shard_frames = dist and args.shard == "frames"
     if shard_frames:
         m.set_frame_sharding(rank, world)

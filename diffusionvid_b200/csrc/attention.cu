@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(128)
 attention_hd32_kernel(const __half* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
                       __half* __restrict__ O, int Lq, int Lk, long q_rs, long k_rs, long v_rs, long o_rs, long q_bs,
                       long k_bs, long v_bs, long o_bs, float scale_log2e) {
+  pdl_prologue();
   __shared__ __align__(128) uint8_t sQ[BQ * ROW_B];
   __shared__ __align__(128) uint8_t sK[2][BK * ROW_B];
   __shared__ __align__(128) uint8_t sV[2][BK * ROW_B];
@@ -211,7 +212,7 @@ int attention_launch(const void* q, const void* k, const void* v, void* o, int b
   if ((q_rs | k_rs | v_rs | q_bs | k_bs | v_bs) % 8 != 0 || (o_rs | o_bs) % 2 != 0) return DVID_ERR_SHAPE;
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   dim3 grid((lq + BQ - 1) / BQ, heads, batch);
-  attention_hd32_kernel<<<grid, 128, 0, stream>>>(
+  launch_pdl(attention_hd32_kernel, dim3(grid), dim3(128), 0, stream, 
       static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v),
       static_cast<__half*>(o), lq, lk, q_rs, k_rs, v_rs, o_rs, q_bs, k_bs, v_bs, o_bs, scale_log2e);
   return check_launch();

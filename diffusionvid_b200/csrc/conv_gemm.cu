@@ -109,6 +109,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  pdl_trigger();   // the next kernel of the stream may start its prologue while this one runs (see dvid_internal.h)
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -147,6 +148,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int tw = 1 << p.tw_log2;
@@ -548,6 +550,15 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
   return 0;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DVID_PDL");
+    v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return v != 0;
+}
+
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -577,7 +588,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     const size_t bytes = 3 * 2048 * sizeof(unsigned long long);
     cudaMalloc(&q.trace, bytes);
     cudaMemsetAsync(q.trace, 0, bytes, stream);
-    conv_gemm_kernel<BN, BSTAT, RES><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, q);
+    launch_pdl(conv_gemm_kernel<BN, BSTAT, RES>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, q);
     cudaStreamSynchronize(stream);
     static unsigned long long host[3 * 2048];
     cudaMemcpy(host, q.trace, bytes, cudaMemcpyDeviceToHost);
@@ -595,7 +606,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
       }
     return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
   }
-  conv_gemm_kernel<BN, BSTAT, RES><<<grid, 384, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmR, p);
+  launch_pdl(conv_gemm_kernel<BN, BSTAT, RES>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, p);
   return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
 }
 

@@ -85,6 +85,40 @@ int swin_patch_gather_launch(const float* img, void* out, int B, int H, int W, c
 int swin_window_attention_launch(const void* qkv, const float* bias, void* out, int B, int H, int W, int C, int heads,
                                  int shift, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the library is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_prologue(): `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be
+// scheduled (and run its own prologue: barrier init, TMEM allocation, descriptor prefetch) while this one drains,
+// `griddepcontrol.wait` blocks until the PREVIOUS kernel has completed and its writes are visible.  No global memory
+// may be touched before the wait.  The hot path is ~5000 short dependent kernels per clip, so the launch-to-launch
+// bubble matters.  DVID_PDL=0 launches without the attribute (the two instructions are then no-ops).
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 inline int check_launch() { return cudaGetLastError() == cudaSuccess ? DVID_OK : DVID_ERR_CUDA; }
 
 }  // namespace dvid

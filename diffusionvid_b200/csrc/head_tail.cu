@@ -70,6 +70,7 @@ head_tail_kernel(const __grid_constant__ TailMaps tm, const TailParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TM;
+  pdl_trigger();
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm.a);
@@ -90,6 +91,7 @@ head_tail_kernel(const __grid_constant__ TailMaps tm, const TailParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -316,7 +318,7 @@ int head_tail_launch(const void* fc, const void* cls_w, const float* cls_g, cons
   for (int i = 0; i < 3; ++i) { p.ln_g[1 + i] = reg_g[i]; p.ln_b[1 + i] = reg_b[i]; }
   p.cls_bias = logit_bias; p.delta_bias = delta_bias; p.boxes_in = boxes_in;
   p.logits_out = logits_out; p.boxes_out = boxes_out;
-  head_tail_kernel<<<(M + TM - 1) / TM, 256, SMEM_BYTES, stream>>>(tm, p);
+  launch_pdl(head_tail_kernel, dim3((M + TM - 1) / TM), dim3(256), SMEM_BYTES, stream, tm, p);
   return check_launch();
 }
 

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(1024)
 topk_scores_kernel(const float* __restrict__ logits, const float* __restrict__ boxes, int N, int C, int k,
                    float* __restrict__ out_boxes, float* __restrict__ out_scores, int* __restrict__ out_labels,
                    int cap, int slot0) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char tk_smem[];
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(tk_smem);        // 1024 selected keys
   unsigned* su = reinterpret_cast<unsigned*>(tk_smem + 1024 * 8);                      // N*C score bit patterns
@@ -151,6 +152,7 @@ topk_scores_kernel(const float* __restrict__ logits, const float* __restrict__ b
 __global__ void __launch_bounds__(1024)
 topk_mask_kernel(const float* __restrict__ logits, int N, int C, int k1, int k2, unsigned char* __restrict__ mask1,
                  unsigned char* __restrict__ mask2) {
+  pdl_prologue();
   __shared__ unsigned long long skeys[1024];
   const int f = blockIdx.x;
   const int i = threadIdx.x;
@@ -178,6 +180,7 @@ topk_mask_kernel(const float* __restrict__ logits, int N, int C, int k1, int k2,
 __global__ void __launch_bounds__(1024)
 gather_masked_rows_kernel(const float* __restrict__ src, const unsigned char* __restrict__ mask, int N, int k,
                           float* __restrict__ dst) {
+  pdl_prologue();
   __shared__ int spos[1024];
   __shared__ int wcnt[32];
   const int f = blockIdx.x, i = threadIdx.x, lane = i & 31, warp = i >> 5;
@@ -226,6 +229,7 @@ constexpr int NMS_MAX = 1024;
 constexpr int NMS_WORDS = NMS_MAX / 64;
 
 __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char nms_smem[];
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(nms_smem);             // 1024 keys
   float4* sbox = reinterpret_cast<float4*>(nms_smem + NMS_MAX * 8);                        // 1024 sorted boxes
@@ -391,6 +395,7 @@ __global__ void __launch_bounds__(1024) nms_kernel(const NmsArgs a) {
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const float4* __restrict__ ws_boxes, const int* __restrict__ counts, int n_fixed, int cap, float thr,
                 int plus_one, int ge, unsigned long long* __restrict__ ws_mask) {
+  pdl_prologue();
   const int f = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -426,6 +431,7 @@ nms_mask_kernel(const float4* __restrict__ ws_boxes, const int* __restrict__ cou
 // ------------------------------------------------------------------------------------------------ cdist + FPS
 // out[i][j] = sqrt(sum_k (x[i][k] - x[j][k])^2), fp32, direct differences (torch.cdist p=2 without the matmul trick).
 __global__ void __launch_bounds__(256) cdist_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int d) {
+  pdl_prologue();
   __shared__ float sa[32][33];
   __shared__ float sb[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -468,6 +474,7 @@ constexpr int FPS_PER_THREAD = 8;   // n <= 8192
 __global__ void __launch_bounds__(1024)
 fps_kernel(int n, int m, int log2_bs, const float* __restrict__ dist, float* __restrict__ temp,
            int* __restrict__ idx) {
+  pdl_prologue();
   __shared__ float sval[32];
   __shared__ unsigned sprio[32];
   __shared__ int sold;
@@ -550,7 +557,7 @@ int topk_scores_launch(const float* logits, const float* boxes, int frames, int 
       return DVID_ERR_CUDA;
     attr_set = true;
   }
-  topk_scores_kernel<<<frames, 1024, smem, stream>>>(logits, boxes, N, C, k, out_boxes, out_scores, out_labels, cap,
+  launch_pdl(topk_scores_kernel, dim3(frames), dim3(1024), smem, stream, logits, boxes, N, C, k, out_boxes, out_scores, out_labels, cap,
                                                      slot0);
   return check_launch();
 }
@@ -558,14 +565,14 @@ int topk_scores_launch(const float* logits, const float* boxes, int frames, int 
 int topk_mask_launch(const float* logits, int frames, int N, int C, int k1, int k2, unsigned char* mask1,
                      unsigned char* mask2, cudaStream_t stream) {
   if (frames <= 0 || N <= 0 || N > 1024 || k1 > N || k2 > k1 || k2 < 0) return DVID_ERR_SHAPE;
-  topk_mask_kernel<<<frames, 1024, 0, stream>>>(logits, N, C, k1, k2, mask1, mask2);
+  launch_pdl(topk_mask_kernel, dim3(frames), dim3(1024), 0, stream, logits, N, C, k1, k2, mask1, mask2);
   return check_launch();
 }
 
 int gather_masked_rows_launch(const float* src, const unsigned char* mask, int frames, int N, int k, float* dst,
                               cudaStream_t stream) {
   if (frames <= 0 || N <= 0 || N > 1024 || k <= 0) return DVID_ERR_SHAPE;
-  gather_masked_rows_kernel<<<frames, 1024, 0, stream>>>(src, mask, N, k, dst);
+  launch_pdl(gather_masked_rows_kernel, dim3(frames), dim3(1024), 0, stream, src, mask, N, k, dst);
   return check_launch();
 }
 
@@ -596,21 +603,21 @@ int nms_launch(const float* boxes, const float* scores, const int* labels, const
     a.ws_boxes = reinterpret_cast<float4*>(w + static_cast<size_t>(frames) * NMS_MAX * 8);
     a.ws_mask = reinterpret_cast<unsigned long long*>(w + static_cast<size_t>(frames) * NMS_MAX * 24);
     a.phase = 1;
-    nms_kernel<<<frames, 1024, smem, stream>>>(a);
+    launch_pdl(nms_kernel, dim3(frames), dim3(1024), smem, stream, a);
     dim3 grid((NMS_MAX + 7) / 8, frames);
-    nms_mask_kernel<<<grid, 256, 0, stream>>>(a.ws_boxes, counts, n, cap, thr, plus_one, ge, a.ws_mask);
+    launch_pdl(nms_mask_kernel, dim3(grid), dim3(256), 0, stream, a.ws_boxes, counts, n, cap, thr, plus_one, ge, a.ws_mask);
     a.phase = 2;
-    nms_kernel<<<frames, 1024, smem, stream>>>(a);
+    launch_pdl(nms_kernel, dim3(frames), dim3(1024), smem, stream, a);
     return check_launch();
   }
-  nms_kernel<<<frames, 1024, smem, stream>>>(a);
+  launch_pdl(nms_kernel, dim3(frames), dim3(1024), smem, stream, a);
   return check_launch();
 }
 
 int cdist_launch(const float* x, float* out, int n, int d, cudaStream_t stream) {
   if (n <= 0 || d <= 0) return DVID_ERR_SHAPE;
   dim3 grid((n + 31) / 32, (n + 31) / 32);
-  cdist_kernel<<<grid, 256, 0, stream>>>(x, out, n, d);
+  launch_pdl(cdist_kernel, dim3(grid), dim3(256), 0, stream, x, out, n, d);
   return check_launch();
 }
 
@@ -620,7 +627,7 @@ int fps_launch(int b, int n, int m, const float* dist, float* temp, int* idx, cu
   int p = 0;
   while ((2 << p) <= n) ++p;           // floor(log2 n): opt_n_threads of the reference (fps.cu:11-15)
   if (p > 10) p = 10;
-  fps_kernel<<<b, 1024, 0, stream>>>(n, m, p, dist, temp, idx);
+  launch_pdl(fps_kernel, dim3(b), dim3(1024), 0, stream, n, m, p, dist, temp, idx);
   return check_launch();
 }
 

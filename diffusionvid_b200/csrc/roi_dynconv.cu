@@ -160,6 +160,7 @@ __device__ __forceinline__ uint4 pack8(const float (&a)[8]) {
 __global__ void __launch_bounds__(256)
 roi_align_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_frame, __half* __restrict__ roi_out,
                  float* __restrict__ mean_f32, __half* __restrict__ mean_f16) {
+  pdl_prologue();
   __shared__ float sred[8][D];
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -223,7 +224,8 @@ roi_dynconv_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_
                    const __half* __restrict__ params,      // [M][2*256*64]: P1 [256][64] then P2 [64][256]
                    const float* __restrict__ g1, const float* __restrict__ b1,   // LayerNorm(64)
                    const float* __restrict__ g2, const float* __restrict__ b2,   // LayerNorm(256)
-                   __half* __restrict__ out) {              // [M][49][256]
+                   __half* __restrict__ out) {
+  pdl_prologue();              // [M][49][256]
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sRoi = smem + SM_ROI;
   uint8_t* sP1 = smem + SM_P1;
@@ -408,7 +410,7 @@ int roi_align_launch(const void* const* feats, const int* hs, const int* ws, con
                      int num_boxes, int boxes_per_frame, void* roi_out, float* mean_f32, void* mean_f16,
                      cudaStream_t stream) {
   if (num_boxes <= 0 || boxes_per_frame <= 0) return DVID_ERR_SHAPE;
-  roi_align_kernel<<<num_boxes, 256, 0, stream>>>(make_levels(feats, hs, ws, scales), boxes, boxes_per_frame,
+  launch_pdl(roi_align_kernel, dim3(num_boxes), dim3(256), 0, stream, make_levels(feats, hs, ws, scales), boxes, boxes_per_frame,
                                                   static_cast<__half*>(roi_out), mean_f32,
                                                   static_cast<__half*>(mean_f16));
   return check_launch();
@@ -430,11 +432,11 @@ int roi_dynconv_launch(const void* const* feats, const int* hs, const int* ws, c
   }
   const RoiLevels lv = make_levels(feats, hs, ws, scales);
   if (roi_in != nullptr) {
-    roi_dynconv_kernel<true><<<num_boxes, 256, SM_TOTAL, stream>>>(
+    launch_pdl(roi_dynconv_kernel<true>, dim3(num_boxes), dim3(256), SM_TOTAL, stream, 
         lv, boxes, boxes_per_frame, static_cast<const __half*>(roi_in), static_cast<const __half*>(params), g1, b1,
         g2, b2, static_cast<__half*>(out));
   } else {
-    roi_dynconv_kernel<false><<<num_boxes, 256, SM_TOTAL, stream>>>(
+    launch_pdl(roi_dynconv_kernel<false>, dim3(num_boxes), dim3(256), SM_TOTAL, stream, 
         lv, boxes, boxes_per_frame, nullptr, static_cast<const __half*>(params), g1, b1, g2, b2,
         static_cast<__half*>(out));
   }

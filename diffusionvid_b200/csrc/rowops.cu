@@ -14,6 +14,7 @@ namespace {
 // NHWC fp16 with 8 channels (3 real + 5 zero) and a zero halo of `halo` pixels (the stem convolution's padding).
 __global__ void preprocess_kernel(const float* __restrict__ img, __half* __restrict__ out, int n, int H, int W, int halo,
                                   int Hp, int Wp, float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_prologue();
   const long total = static_cast<long>(n) * Hp * Wp;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -38,6 +39,7 @@ __global__ void preprocess_kernel(const float* __restrict__ img, __half* __restr
 // ------------------------------------------------------------------------------------------------ maxpool 3x3 s2 p1
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n, int H, int W, int C,
                                     int Ho, int Wo) {
+  pdl_prologue();
   const int cg = C / 8;
   const long total = static_cast<long>(n) * Ho * Wo * cg;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -123,6 +125,7 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
 __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(256) row_post_kernel(const RowPostArgs a) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= a.M) return;
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(256) row_post_kernel(const RowPostArgs a) {
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ a, const __half* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ out, int m, int n, int k, int act_in, int act_out) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (col >= n) return;
@@ -246,6 +250,7 @@ small_linear_kernel(const float* __restrict__ a, const __half* __restrict__ w, c
 // `freq` = exp(arange(128) * -(ln 10000 / 127)) is passed in (computed once by the host exactly as the reference does).
 __global__ void time_sinusoid_kernel(const float* __restrict__ t, const float* __restrict__ freq,
                                      float* __restrict__ out, int m) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m * 128) return;
   const int r = i / 128, kx = i % 128;
@@ -263,6 +268,7 @@ __global__ void head_final_kernel(const float* __restrict__ logit_part, int ldl,
                                   int C, const float* __restrict__ delta_part, int ldd,
                                   const float* __restrict__ delta_bias, const float* __restrict__ boxes_in,
                                   float* __restrict__ logits_out, float* __restrict__ boxes_out, int M) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   for (int c = 0; c < C; ++c) logits_out[static_cast<long>(i) * C + c] = logit_part[static_cast<long>(i) * ldl + c] + cls_bias[c];
@@ -300,6 +306,7 @@ __device__ __forceinline__ float4 noise_to_box(float4 x, float scale, float W, f
 
 __global__ void noise_to_boxes_kernel(const float* __restrict__ x, float* __restrict__ boxes, int M, float scale,
                                       float W, float H) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M) return;
   *reinterpret_cast<float4*>(boxes + static_cast<long>(i) * 4) =
@@ -317,6 +324,7 @@ ddim_step_kernel(const float* __restrict__ logits, int C, const float* __restric
                  float* __restrict__ x_next, float* __restrict__ boxes_next, int* __restrict__ num_kept, int N,
                  float scale, float W, float H, float sqrt_recip_a, float sqrt_recipm1_a, float sqrt_a_next, float c_coef,
                  float sigma) {
+  pdl_prologue();
   __shared__ int warp_cnt[32];
   __shared__ int warp_off[33];
   const int f = blockIdx.x;
@@ -393,7 +401,7 @@ int preprocess_launch(const float* img, void* out, int n, int H, int W, int halo
                       const float* std, cudaStream_t stream) {
   if (n <= 0 || H <= 0 || W <= 0 || Hp < H + 2 * halo || Wp < W + 2 * halo) return DVID_ERR_SHAPE;
   const long total = static_cast<long>(n) * Hp * Wp;
-  preprocess_kernel<<<grid_for(total, 256), 256, 0, stream>>>(img, static_cast<__half*>(out), n, H, W, halo, Hp, Wp,
+  launch_pdl(preprocess_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, img, static_cast<__half*>(out), n, H, W, halo, Hp, Wp,
                                                               mean[0], mean[1], mean[2], std[0], std[1], std[2]);
   return check_launch();
 }
@@ -402,7 +410,7 @@ int maxpool_launch(const void* in, void* out, int n, int H, int W, int C, cudaSt
   if (n <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return DVID_ERR_SHAPE;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long total = static_cast<long>(n) * Ho * Wo * (C / 8);
-  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __half*>(in),
+  launch_pdl(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, static_cast<const __half*>(in),
                                                                 static_cast<__half*>(out), n, H, W, C, Ho, Wo);
   return check_launch();
 }
@@ -423,21 +431,21 @@ int row_post_launch(const float* partials, int splits, long split_stride, const 
   a.mod_scale = mod_scale; a.mod_shift = mod_shift; a.rows_per_group = rows_per_group; a.scale_stride = scale_stride;
   a.shift_stride = shift_stride; a.shift_per_row = shift_per_row; a.out_mod_f16 = static_cast<__half*>(out_mod_f16);
   a.M = M;
-  row_post_kernel<<<(M + 7) / 8, 256, 0, stream>>>(a);
+  launch_pdl(row_post_kernel, dim3((M + 7) / 8), dim3(256), 0, stream, a);
   return check_launch();
 }
 
 int small_linear_launch(const float* a, const void* w, const float* bias, float* out, int m, int n, int k, int act_in,
                         int act_out, cudaStream_t stream) {
   if (m <= 0 || m > 8 || n <= 0 || k <= 0 || k % 8 != 0) return DVID_ERR_SHAPE;
-  small_linear_kernel<<<(n + 7) / 8, 256, 0, stream>>>(a, static_cast<const __half*>(w), bias, out, m, n, k, act_in,
+  launch_pdl(small_linear_kernel, dim3((n + 7) / 8), dim3(256), 0, stream, a, static_cast<const __half*>(w), bias, out, m, n, k, act_in,
                                                         act_out);
   return check_launch();
 }
 
 int time_sinusoid_launch(const float* t, const float* freq, float* out, int m, cudaStream_t stream) {
   if (m <= 0) return DVID_ERR_SHAPE;
-  time_sinusoid_kernel<<<(m * 128 + 127) / 128, 128, 0, stream>>>(t, freq, out, m);
+  launch_pdl(time_sinusoid_kernel, dim3((m * 128 + 127) / 128), dim3(128), 0, stream, t, freq, out, m);
   return check_launch();
 }
 
@@ -445,14 +453,14 @@ int head_final_launch(const float* logit_part, int ldl, const float* cls_bias, i
                       const float* delta_bias, const float* boxes_in, float* logits_out, float* boxes_out, int M,
                       cudaStream_t stream) {
   if (M <= 0 || C <= 0 || C > ldl || ldd < 4) return DVID_ERR_SHAPE;
-  head_final_kernel<<<(M + 127) / 128, 128, 0, stream>>>(logit_part, ldl, cls_bias, C, delta_part, ldd, delta_bias,
+  launch_pdl(head_final_kernel, dim3((M + 127) / 128), dim3(128), 0, stream, logit_part, ldl, cls_bias, C, delta_part, ldd, delta_bias,
                                                         boxes_in, logits_out, boxes_out, M);
   return check_launch();
 }
 
 int noise_to_boxes_launch(const float* x, float* boxes, int M, float scale, float W, float H, cudaStream_t stream) {
   if (M <= 0) return DVID_ERR_SHAPE;
-  noise_to_boxes_kernel<<<(M + 127) / 128, 128, 0, stream>>>(x, boxes, M, scale, W, H);
+  launch_pdl(noise_to_boxes_kernel, dim3((M + 127) / 128), dim3(128), 0, stream, x, boxes, M, scale, W, H);
   return check_launch();
 }
 
@@ -461,7 +469,7 @@ int ddim_step_launch(const float* logits, int C, const float* coord, const float
                      float scale, float W, float H, float sqrt_recip_a, float sqrt_recipm1_a, float sqrt_a_next,
                      float c_coef, float sigma, cudaStream_t stream) {
   if (frames <= 0 || N <= 0 || N > 1024) return DVID_ERR_SHAPE;
-  ddim_step_kernel<<<frames, 1024, 0, stream>>>(logits, C, coord, x_t, eps, fill, x_next, boxes_next, num_kept, N,
+  launch_pdl(ddim_step_kernel, dim3(frames), dim3(1024), 0, stream, logits, C, coord, x_t, eps, fill, x_next, boxes_next, num_kept, N,
                                                scale, W, H, sqrt_recip_a, sqrt_recipm1_a, sqrt_a_next, c_coef, sigma);
   return check_launch();
 }

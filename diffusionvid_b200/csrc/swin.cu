@@ -62,6 +62,7 @@ struct RowArgs {
 // One warp per row.  V4 = C / 128 float4 groups per lane, group j of lane l covers channels (j*32 + l)*4 .. +3.
 template <int V4>
 __global__ void __launch_bounds__(256) swin_rows_kernel(const RowArgs a) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= a.rows) return;
@@ -155,6 +156,7 @@ template <int V4>
 __global__ void __launch_bounds__(256)
 swin_merge_kernel(const float* __restrict__ X, int B, int H, int W, int C, const float* __restrict__ gamma,
                   const float* __restrict__ beta, __half* __restrict__ out) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
   const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -198,6 +200,7 @@ swin_merge_kernel(const float* __restrict__ X, int B, int H, int W, int C, const
 // out [B*(H/4)*(W/4)][64] fp16, k = c*16 + py*4 + px (the flattening of proj.weight[embed][3][4][4]), k >= 48 zero.
 __global__ void swin_patch_gather_kernel(const float* __restrict__ img, __half* __restrict__ out, int B, int H, int W,
                                          float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_prologue();
   const int H4 = H / 4, W4 = W / 4;
   const long total = static_cast<long>(B) * H4 * W4 * 4;     // 4 threads per token: thread q writes k in [16q, 16q+16)
   const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
@@ -240,6 +243,7 @@ __device__ __forceinline__ uint32_t wt_off(int row, int chunk) {
 __global__ void __launch_bounds__(128)
 swin_window_attention_kernel(const __half* __restrict__ qkv, const float* __restrict__ bias, __half* __restrict__ out,
                              int C, int nwy, int nwx, int Hp, int Wp, int shift, float scale_log2e) {
+  pdl_prologue();
   __shared__ __align__(128) uint8_t sQ[64 * ROW_B];
   __shared__ __align__(128) uint8_t sK[64 * ROW_B];
   __shared__ __align__(128) uint8_t sV[64 * ROW_B];
@@ -393,11 +397,11 @@ int swin_rows_launch(float* X, int write_x, const void* add, int add_mode, const
   a.rows = out_mode == 2 ? static_cast<long>(B) * a.g.nwy * a.g.nwx * WT : static_cast<long>(B) * H * W;
   const unsigned grid = static_cast<unsigned>((a.rows + 7) / 8);
   switch (C / 128) {
-    case 1: swin_rows_kernel<1><<<grid, 256, 0, stream>>>(a); break;
-    case 2: swin_rows_kernel<2><<<grid, 256, 0, stream>>>(a); break;
-    case 4: swin_rows_kernel<4><<<grid, 256, 0, stream>>>(a); break;
-    case 8: swin_rows_kernel<8><<<grid, 256, 0, stream>>>(a); break;
-    case 16: swin_rows_kernel<16><<<grid, 256, 0, stream>>>(a); break;
+    case 1: launch_pdl(swin_rows_kernel<1>, dim3(grid), dim3(256), 0, stream, a); break;
+    case 2: launch_pdl(swin_rows_kernel<2>, dim3(grid), dim3(256), 0, stream, a); break;
+    case 4: launch_pdl(swin_rows_kernel<4>, dim3(grid), dim3(256), 0, stream, a); break;
+    case 8: launch_pdl(swin_rows_kernel<8>, dim3(grid), dim3(256), 0, stream, a); break;
+    case 16: launch_pdl(swin_rows_kernel<16>, dim3(grid), dim3(256), 0, stream, a); break;
     default: return DVID_ERR_SHAPE;
   }
   return check_launch();
@@ -410,9 +414,9 @@ int swin_merge_launch(const float* X, int B, int H, int W, int C, const float* g
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   __half* o = static_cast<__half*>(out);
   switch (4 * C / 128) {
-    case 4: swin_merge_kernel<4><<<grid, 256, 0, stream>>>(X, B, H, W, C, gamma, beta, o); break;
-    case 8: swin_merge_kernel<8><<<grid, 256, 0, stream>>>(X, B, H, W, C, gamma, beta, o); break;
-    case 16: swin_merge_kernel<16><<<grid, 256, 0, stream>>>(X, B, H, W, C, gamma, beta, o); break;
+    case 4: launch_pdl(swin_merge_kernel<4>, dim3(grid), dim3(256), 0, stream, X, B, H, W, C, gamma, beta, o); break;
+    case 8: launch_pdl(swin_merge_kernel<8>, dim3(grid), dim3(256), 0, stream, X, B, H, W, C, gamma, beta, o); break;
+    case 16: launch_pdl(swin_merge_kernel<16>, dim3(grid), dim3(256), 0, stream, X, B, H, W, C, gamma, beta, o); break;
     default: return DVID_ERR_SHAPE;
   }
   return check_launch();
@@ -422,7 +426,7 @@ int swin_patch_gather_launch(const float* img, void* out, int B, int H, int W, c
                              cudaStream_t stream) {
   if (B <= 0 || H % 4 != 0 || W % 4 != 0) return DVID_ERR_SHAPE;
   const long total = static_cast<long>(B) * (H / 4) * (W / 4) * 4;
-  swin_patch_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+  launch_pdl(swin_patch_gather_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 
       img, static_cast<__half*>(out), B, H, W, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
   return check_launch();
 }
@@ -435,7 +439,7 @@ int swin_window_attention_launch(const void* qkv, const float* bias, void* out, 
   if (wins > 2147483647L || heads > 65535) return DVID_ERR_SHAPE;
   const float scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   dim3 grid(static_cast<unsigned>(wins), heads);
-  swin_window_attention_kernel<<<grid, 128, 0, stream>>>(static_cast<const __half*>(qkv), bias,
+  launch_pdl(swin_window_attention_kernel, dim3(grid), dim3(128), 0, stream, static_cast<const __half*>(qkv), bias,
                                                          static_cast<__half*>(out), C, nwy, nwx, nwy * WS, nwx * WS,
                                                          shift, scale_log2e);
   return check_launch();

@@ -101,7 +101,7 @@ class DiffusionDet(nn.Module):
         # execution policy (CUDA only): captured graphs per unit, frames of a batch spread over parallel streams
         self.use_graphs = bool(hp.get("use_graphs", True))
         self.use_streams = bool(hp.get("use_streams", True))
-        self.frames_per_stream = int(hp.get("frames_per_stream", 4))
+        self.frames_per_stream = int(hp.get("frames_per_stream", 8))
         self.debug_trace = False
         self.fused_tail = bool(hp.get("fused_tail", True))
         self._graphs = {}
