@@ -12,6 +12,7 @@
 // Two kernels share the gather code:
 //   roi_align_kernel      : ROI tile -> global (and the per-box mean that seeds pro_features, box_head.py:509-510)
 //   roi_dynconv_kernel<G> : G=false gathers the ROI tile itself (fused ROIAlign), G=true reads it from global.
+#include <stdlib.h>
 #include "dvid_internal.h"
 #include "warp_mma.cuh"
 
@@ -113,6 +114,7 @@ __device__ __forceinline__ RoiGeom roi_geometry(const RoiLevels& lv, const float
 }
 
 // Gather one 7x7 bin (all 256 channels) with the calling warp: lane owns channels [8*lane, 8*lane+8).
+template <bool kDeep>
 __device__ __forceinline__ void roi_bin(const RoiGeom& gm, int bin, int lane, float (&acc)[8]) {
   const int ph = bin / P, pw = bin - ph * P;
   AxisTaps ty, tx;
@@ -120,25 +122,58 @@ __device__ __forceinline__ void roi_bin(const RoiGeom& gm, int bin, int lane, fl
   axis_taps(gm.x1, gm.bw, pw, gm.W, tx);
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (kDeep) {
+    // all (up to 16) taps of the bin are requested before the first one is consumed: inside the fused kernel (2 CTAs
+    // per SM) the gather is bound by the number of 512-byte requests in flight, not by arithmetic
+    uint4 v[4][4];
 #pragma unroll
-  for (int iy = 0; iy < 4; ++iy) {
-    if (ty.w[iy] == 0.f) continue;   // warp-uniform
-    const __half* rowp = gm.feat + static_cast<long>(ty.idx[iy]) * gm.W * D + lane * 8;
-    uint4 v[4];
+    for (int iy = 0; iy < 4; ++iy) {
+      if (ty.w[iy] == 0.f) continue;   // warp-uniform
+      const __half* rowp = gm.feat + static_cast<long>(ty.idx[iy]) * gm.W * D + lane * 8;
 #pragma unroll
-    for (int ix = 0; ix < 4; ++ix) {
-      if (tx.w[ix] != 0.f) v[ix] = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long>(tx.idx[ix]) * D));
+      for (int ix = 0; ix < 4; ++ix) {
+        if (tx.w[ix] != 0.f) v[iy][ix] = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long>(tx.idx[ix]) * D));
+      }
     }
 #pragma unroll
-    for (int ix = 0; ix < 4; ++ix) {
-      if (tx.w[ix] != 0.f) {
-        const float wgt = ty.w[iy] * tx.w[ix];
-        const __half2* hp = reinterpret_cast<const __half2*>(&v[ix]);
+    for (int iy = 0; iy < 4; ++iy) {
+      if (ty.w[iy] == 0.f) continue;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(hp[e]);
-          acc[2 * e] = fmaf(wgt, f.x, acc[2 * e]);
-          acc[2 * e + 1] = fmaf(wgt, f.y, acc[2 * e + 1]);
+      for (int ix = 0; ix < 4; ++ix) {
+        if (tx.w[ix] != 0.f) {
+          const float wgt = ty.w[iy] * tx.w[ix];
+          const __half2* hp = reinterpret_cast<const __half2*>(&v[iy][ix]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hp[e]);
+            acc[2 * e] = fmaf(wgt, f.x, acc[2 * e]);
+            acc[2 * e + 1] = fmaf(wgt, f.y, acc[2 * e + 1]);
+          }
+        }
+      }
+    }
+  } else {
+    // one tap row at a time (few registers: the stand-alone ROIAlign kernel runs at full occupancy instead)
+#pragma unroll
+    for (int iy = 0; iy < 4; ++iy) {
+      if (ty.w[iy] == 0.f) continue;   // warp-uniform
+      const __half* rowp = gm.feat + static_cast<long>(ty.idx[iy]) * gm.W * D + lane * 8;
+      uint4 v[4];
+#pragma unroll
+      for (int ix = 0; ix < 4; ++ix) {
+        if (tx.w[ix] != 0.f) v[ix] = __ldg(reinterpret_cast<const uint4*>(rowp + static_cast<long>(tx.idx[ix]) * D));
+      }
+#pragma unroll
+      for (int ix = 0; ix < 4; ++ix) {
+        if (tx.w[ix] != 0.f) {
+          const float wgt = ty.w[iy] * tx.w[ix];
+          const __half2* hp = reinterpret_cast<const __half2*>(&v[ix]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hp[e]);
+            acc[2 * e] = fmaf(wgt, f.x, acc[2 * e]);
+            acc[2 * e + 1] = fmaf(wgt, f.y, acc[2 * e + 1]);
+          }
         }
       }
     }
@@ -170,7 +205,7 @@ roi_align_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_fr
   for (int e = 0; e < 8; ++e) msum[e] = 0.f;
   for (int bin = warp; bin < NBIN; bin += 8) {
     float acc[8];
-    roi_bin(gm, bin, lane, acc);
+    roi_bin<false>(gm, bin, lane, acc);
     const uint4 pk = pack8(acc);
     if (roi_out) *reinterpret_cast<uint4*>(roi_out + (static_cast<long>(b) * NBIN + bin) * D + lane * 8) = pk;
     const __half2* hp = reinterpret_cast<const __half2*>(&pk);
@@ -267,7 +302,7 @@ roi_dynconv_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_
     const RoiGeom gm = roi_geometry(lv, boxes, b, boxes_per_frame);
     for (int bin = warp; bin < NBIN; bin += 8) {
       float acc[8];
-      roi_bin(gm, bin, lane, acc);
+      roi_bin<true>(gm, bin, lane, acc);
       *reinterpret_cast<uint4*>(sRoi + off512(bin, lane)) = pack8(acc);
     }
   }
