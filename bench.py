@@ -289,7 +289,12 @@ def run_ours(args):
             ops.PROFILE = None
             m.use_graphs, m.use_streams = ug, us
             fam = {}
+            shapes = []
             for k, (evs, flops, nbytes) in prof.items():
+                if ":" in k:      # per-shape entry (tools/profile_shapes.py prints these in full)
+                    t = sum(s.elapsed_time(e) for s, e in evs)
+                    shapes.append((t, k, len(evs), flops))
+                    continue
                 t = sum(s.elapsed_time(e) for s, e in evs)
                 fam[k] = {"ms": t, "launches": len(evs), "tflops": flops / t / 1e9 if t > 0 else 0.0,
                           "gbs": nbytes / t / 1e6 if t > 0 else 0.0}
@@ -301,7 +306,19 @@ def run_ours(args):
                     "frac": cg["tflops"] / peak_tf if peak_tf else None, "peak_source": src, "traffic": None,
                     "launches_per_step": cg["launches"], "avg_launch_us": 1000.0 * cg["ms"] / max(1, cg["launches"]),
                     "share_of_step": cg["ms"] / clip_ms if clip_ms > 0 else None,
-                    "families": {k: {kk: round(vv, 3) for kk, vv in v.items()} for k, v in fam.items()}}
+                    "note": "achieved = algorithmic FLOPs of all conv_gemm_kernel launches of one clip / their summed "
+                            "CUDA-event time (eager instrumented pass); share_of_step relates that eager kernel time "
+                            "to the graph-replayed step",
+                    "families": {k: {kk: round(vv, 3) for kk, vv in v.items()} for k, v in fam.items()},
+                    "top_shapes": [{"shape": k.split(":", 1)[1], "launches": n, "ms": round(t, 3),
+                                    "tflops": round(fl / t / 1e9, 1) if t > 0 else 0.0}
+                                   for t, k, n, fl in sorted(shapes, reverse=True)[:8]]}
+            tf = os.path.join(ROOT, "profiles", "conv_gemm_traffic.json")
+            if os.path.exists(tf):       # dram bytes per launch from the committed ncu --set full capture
+                with open(tf) as f:
+                    tj = json.load(f)
+                roof["traffic"] = tj.get("dram_bytes_per_launch")
+                roof["traffic_source"] = tj.get("source")
 
     mult = 1 if shard_frames else world       # frame sharding: all ranks work on the same clip
     total_frames = frames * mult
