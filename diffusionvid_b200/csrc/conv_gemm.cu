@@ -666,6 +666,29 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   if (out_f32 != nullptr && !(p.h_out == 1 && n == 1 && p.th == 1)) return DVID_ERR_SHAPE;  // GEMM view only
 
   int bn = force_bn;
+  {
+    static int env_bn = -1;
+    if (env_bn < 0) { const char* e = getenv("DVID_FORCE_BN"); env_bn = e ? atoi(e) : 0; }
+    if (bn == 0 && env_bn > 0 && cout >= env_bn) bn = env_bn;
+  }
+  static int cost_model = -1;
+  if (cost_model < 0) { const char* e = getenv("DVID_BN_COST"); cost_model = e ? atoi(e) : 1; }
+  if (bn == 0 && cost_model) {
+    // Tile width by a wave-quantisation cost model: waves(bn) x relative tile cost.  The costs are measured on B200
+    // (tools/bench_gemm.py with DVID_FORCE_BN): a 128-wide tile costs ~0.78 of a 256-wide one (the A tile is re-read
+    // from smem per MMA, same epilogue overheads), a 64-wide one ~0.55.  Example: res5 3x3 conv, 38 M tiles x 512
+    // channels: bn=256 -> 1 wave x 1.0 (37.9 us), bn=128 -> 2 waves x 0.78 (52.2 us).
+    const double tile_cost[3] = {1.0, 0.78, 0.55};
+    const int cand[3] = {256, 128, 64};
+    double best = 1e30;
+    for (int i = 0; i < 3; ++i) {
+      if (cand[i] > 64 && cout < cand[i]) continue;
+      const long long tiles = static_cast<long long>(p.m_tiles) * p.splits * ((cout + cand[i] - 1) / cand[i]);
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      const double c = static_cast<double>(waves) * tile_cost[i];
+      if (c < best * 0.97) { best = c; bn = cand[i]; }     // prefer the wider tile unless clearly worse
+    }
+  }
   if (bn == 0) {
     const long long want = (num_sms() * 4) / 5;
     if (cout >= 256 && static_cast<long long>(p.m_tiles) * p.splits * ((cout + 255) / 256) >= want) bn = 256;

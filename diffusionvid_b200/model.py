@@ -106,6 +106,7 @@ class DiffusionDet(nn.Module):
         self.fused_tail = bool(hp.get("fused_tail", True))
         self._graphs = {}
         self._streams = []
+        self._streams_inner = []
         self._shard = None
         self.eval()
 
@@ -364,16 +365,22 @@ class DiffusionDet(nn.Module):
         roi = None
         if pro32 is None:
             roi, pro32, pro16 = ops.roi_align(lv, boxes, N)
-        # self-attention over the N boxes of each frame
-        qkv = ops.gemm(pro16, e["in_w"], e["in_b"])
-        ctx = torch.empty((M, 256), device=dev, dtype=H)
-        ops.attention(qkv, qkv[:, 256:], qkv[:, 512:], ctx, B, 8, N, N, 768, 768, 768, 256, N * 768, N * 768, N * 768,
-                      N * 256)
-        part, s = ops.gemm_partials(ctx, e["out_w"], 1)
-        p32 = torch.empty((M, 256), device=dev, dtype=F32); p16 = torch.empty((M, 256), device=dev, dtype=H)
-        ops.row_post(M, partials=part, splits=s, bias=e["out_b"], resid=pro32, ln2=e["n1"], out_f32=p32, out_f16=p16)
+
+        def attn_and_params():
+            # self-attention over the N boxes of each frame, then the per-box DynamicConv weights
+            qkv = ops.gemm(pro16, e["in_w"], e["in_b"])
+            ctx = torch.empty((M, 256), device=dev, dtype=H)
+            ops.attention(qkv, qkv[:, 256:], qkv[:, 512:], ctx, B, 8, N, N, 768, 768, 768, 256, N * 768, N * 768,
+                          N * 768, N * 256)
+            part, s = ops.gemm_partials(ctx, e["out_w"], 1)
+            p32 = torch.empty((M, 256), device=dev, dtype=F32); p16 = torch.empty((M, 256), device=dev, dtype=H)
+            ops.row_post(M, partials=part, splits=s, bias=e["out_b"], resid=pro32, ln2=e["n1"], out_f32=p32,
+                         out_f16=p16)
+            return p32, ops.gemm(p16, e["dyn_w"], e["dyn_b"])
+
+        # (running the ROI gather on a parallel stream branch next to this block was measured: slower)
+        p32, params = attn_and_params()
         # instance interaction (DynamicConv)
-        params = ops.gemm(p16, e["dyn_w"], e["dyn_b"])
         f2 = ops.roi_dynconv(lv, boxes, N, params, e["dn1"][0], e["dn1"][1], e["dn2"][0], e["dn2"][1], roi_in=roi)
         part, s = ops.gemm_partials(f2, e["ol_w"], 7)
         o32 = torch.empty((M, 256), device=dev, dtype=F32); o16 = torch.empty((M, 256), device=dev, dtype=H)
@@ -471,23 +478,28 @@ class DiffusionDet(nn.Module):
         return torch.randn((frames, N, 4), device=dev, dtype=F32)
 
     # ------------------------------------------------------------------------------------------ execution units
-    def _fork_join(self, fns):
+    def _fork_join(self, fns, pool="_streams"):
         """Run the independent callables `fns` concurrently, one CUDA stream each (frames never interact inside the
         backbone or the decoder: self-attention is per frame, box_head.py:515-516), and join on the current stream.
         Inside a graph capture this records parallel branches; on CPU (test shim) it runs them in order."""
         if len(fns) == 1 or torch.device(self.device).type != "cuda" or not self.use_streams:
             return [f() for f in fns]
         cur = torch.cuda.current_stream()
-        while len(self._streams) < len(fns):
-            self._streams.append(torch.cuda.Stream())
+        streams = getattr(self, pool)
+        while len(streams) < len(fns):
+            # branch 0 carries the critical chain: give it scheduling priority over the helper branches
+            streams.append(torch.cuda.Stream(priority=-1 if len(streams) == 0 else 0))
         outs = []
-        for f, st in zip(fns, self._streams):
+        for f, st in zip(fns, streams):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 outs.append(f())
-        for st in self._streams[:len(fns)]:
+        for st in streams[:len(fns)]:
             cur.wait_stream(st)
         return outs
+
+    def _can_fork(self):
+        return torch.device(self.device).type == "cuda" and self.use_streams
 
     def _groups(self, B):
         g = max(1, int(self.frames_per_stream))
