@@ -273,8 +273,13 @@ def run_ours(args):
         sampler = ClockSampler(local) if rank == 0 else None
         ms, frames, launches, _ = timed(m, dev_samples, args.steps, False, dist, dev)
         clocks = sampler.stop() if sampler else None
+        m.host_results = True      # e2e: detections are delivered on the host (one packed D2H copy per key batch)
         run_clip(m, host_samples, True)
+        io0 = dict(m.io_bytes)
         ms_e2e, frames_e2e, _, d2h = timed(m, host_samples, args.steps, True, dist, dev)
+        h2d_bytes = (m.io_bytes["h2d"] - io0["h2d"]) // max(1, args.steps)     # counted from the tensors copied
+        d2h = m.io_bytes["d2h"] - io0["d2h"]
+        m.host_results = False
 
         roof = None
         if rank == 0 and not args.no_roofline:

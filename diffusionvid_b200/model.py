@@ -107,6 +107,10 @@ class DiffusionDet(nn.Module):
         self._graphs = {}
         self._streams = []
         self._streams_inner = []
+        self._copy_stream = None
+        self.io_bytes = {"h2d": 0, "d2h": 0}   # bytes moved by the model itself (bench.py reports them)
+        self._host_buf = None
+        self.host_results = bool(hp.get("host_results", False))
         self._shard = None
         self.eval()
 
@@ -659,8 +663,13 @@ class DiffusionDet(nn.Module):
             self.cache = deque(maxlen=hp["all_frame_interval"])
             self._video = infos.get("video_id", 0)
         fid = infos["frame_id"]
+        rank, world = self._shard[:2] if self._shard is not None else (0, 1)
         if fid % ib != 0:
-            self.local_img_queue += ref_l
+            # start the host->device copy of the queued frame now, on the copy stream, so that it overlaps the compute
+            # of the current key batch instead of serialising in front of the next one (this rank's frames only)
+            for il in ref_l:
+                own = len(self.local_img_queue) % world == rank
+                self.local_img_queue.append(self._upload(il, dev) if own else il)
             return []
         ref_l = self.local_img_queue + ref_l
         self.local_img_queue = []
@@ -669,8 +678,6 @@ class DiffusionDet(nn.Module):
         T = hp["sample_step"]
         times = list(reversed(torch.linspace(-1, 999, steps=T + 1).int().tolist()))
         self._warm_constants([999] + times[:-1])
-
-        rank, world = self._shard[:2] if self._shard is not None else (0, 1)
 
         # 1. features + base stages for the new local / global frames
         if ref_l or ref_g:
@@ -682,7 +689,7 @@ class DiffusionDet(nn.Module):
             ex = None
             if mine:
                 # host images are copied one by one (asynchronously when pinned) and concatenated on the device
-                total = torch.cat([all_imgs[i].tensors.to(dev, F32, non_blocking=True) for i in mine])
+                total = torch.cat([self._on_device(all_imgs[i], dev) for i in mine])
                 if world == 1:
                     inits = [self._randn("init", fid, bi, min(ib, n_total - bi * ib), dev)
                              for bi in range((n_total + ib - 1) // ib)]
@@ -753,7 +760,10 @@ class DiffusionDet(nn.Module):
                 r = self._run_unit("decode", self._decode, (w, h), tensors, consts)
         if world > 1:
             r = self._exchange_results(r, own, batch, cap, dev)
+        if self.host_results and dev.type == "cuda":
+            return self._results_on_host(r, batch, cap, w, h)
         counts = r["count"].cpu().tolist()       # the one device->host read of the batch
+        self.io_bytes["d2h"] += 4 * batch
         ob, osc, ol = r["boxes"], r["scores"], r["labels"]
         if self._graph_active() and world == 1:
             ob, osc, ol = ob.clone(), osc.clone(), ol.clone()
@@ -763,6 +773,54 @@ class DiffusionDet(nn.Module):
             bl = BoxList(ob[i, :c], (w, h), mode="xyxy")
             bl.add_field("scores", osc[i, :c])
             bl.add_field("labels", ol[i, :c].long())
+            results.append(bl)
+        return results
+
+    # ------------------------------------------------------------------------------------------ host <-> device
+    def _upload(self, il, dev):
+        """Asynchronous H2D copy of one ImageList on the copy stream; returns (device tensor, event) or the list itself
+        when it already lives on the device / there is no CUDA device (CPU tests)."""
+        t = il.tensors
+        if dev.type != "cuda" or t.is_cuda:
+            return il
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        self.io_bytes["h2d"] += t.numel() * t.element_size()
+        with torch.cuda.stream(self._copy_stream):
+            d = t.to(dev, F32, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return (d, ev)
+
+    def _on_device(self, item, dev):
+        """Device fp32 tensor of a queued frame: waits for its prefetch event or copies now."""
+        if isinstance(item, tuple):
+            d, ev = item
+            torch.cuda.current_stream().wait_event(ev)
+            d.record_stream(torch.cuda.current_stream())
+            return d
+        if not item.tensors.is_cuda:
+            self.io_bytes["h2d"] += item.tensors.numel() * item.tensors.element_size()
+        return item.tensors.to(dev, F32, non_blocking=True)
+
+    def _results_on_host(self, r, batch, cap, w, h):
+        """`host_results` mode: ONE device->host copy per key batch (count | boxes | scores | labels packed in fp32; counts
+        <= cap and labels <= 30 are exact) into pinned memory, BoxLists built from CPU views.  The reference's engine
+        moves every BoxList to the CPU right after the call anyway (mega_core/engine/inference.py:75)."""
+        packed = torch.cat([r["count"].to(F32).view(batch, 1), r["boxes"].reshape(batch, -1), r["scores"],
+                            r["labels"].to(F32)], dim=1)
+        if self._host_buf is None or self._host_buf.shape != packed.shape:
+            self._host_buf = torch.empty(packed.shape, dtype=F32, pin_memory=True)
+        self._host_buf.copy_(packed, non_blocking=True)
+        self.io_bytes["d2h"] += packed.numel() * 4
+        torch.cuda.current_stream().synchronize()
+        hb = self._host_buf.clone()
+        results = []
+        for i in range(batch):
+            c = int(hb[i, 0].item())
+            bl = BoxList(hb[i, 1:1 + 4 * cap].view(cap, 4)[:c], (w, h), mode="xyxy")
+            bl.add_field("scores", hb[i, 1 + 4 * cap:1 + 5 * cap][:c])
+            bl.add_field("labels", hb[i, 1 + 5 * cap:1 + 6 * cap][:c].long())
             results.append(bl)
         return results
 
