@@ -104,6 +104,8 @@ class DiffusionDet(nn.Module):
         self.frames_per_stream = int(hp.get("frames_per_stream", 8))
         self.debug_trace = False
         self.fused_tail = bool(hp.get("fused_tail", True))
+        import os as _os
+        self.extract_batch = int(_os.environ.get("DVID_EXTRACT_BATCH", hp.get("extract_batch", 32)))
         self._graphs = {}
         self._streams = []
         self._streams_inner = []
@@ -704,7 +706,12 @@ class DiffusionDet(nn.Module):
                         rows.append(cache[bi][i % ib:i % ib + 1])
                     box_all = torch.cat(rows)
                 outs = []
-                for split, binit in zip(total.split(ib), box_all.split(ib)):
+                # The reference runs the new frames through the backbone / base stages in splits of INFER_BATCH
+                # (diffusion_det.py:424-460).  Every quantity is per frame (the noise rows above follow the reference's
+                # per-split draw order), so up to `extract_batch` frames go through one unit: at a video start
+                # (8 local + 24 global frames) that fills the GPU far better than four 8-frame passes.
+                eb = max(ib, int(self.extract_batch))
+                for split, binit in zip(total.split(eb), box_all.split(eb)):
                     o = self._run_unit("extract", self._extract, (w, h),
                                        dict(imgs=split.contiguous(), box_init=binit.contiguous()), dict(w=w, h=h))
                     # unit outputs live in graph-owned buffers that the next replay overwrites: keep private copies
