@@ -106,6 +106,7 @@ class DiffusionDet(nn.Module):
         self.fused_tail = bool(hp.get("fused_tail", True))
         import os as _os
         self.extract_batch = int(_os.environ.get("DVID_EXTRACT_BATCH", hp.get("extract_batch", 32)))
+        self.dyn_chunk_frames = int(_os.environ.get("DVID_DYN_CHUNK", hp.get("dyn_chunk_frames", 0)))
         self._graphs = {}
         self._streams = []
         self._streams_inner = []
@@ -382,12 +383,27 @@ class DiffusionDet(nn.Module):
             p32 = torch.empty((M, 256), device=dev, dtype=F32); p16 = torch.empty((M, 256), device=dev, dtype=H)
             ops.row_post(M, partials=part, splits=s, bias=e["out_b"], resid=pro32, ln2=e["n1"], out_f32=p32,
                          out_f16=p16)
-            return p32, ops.gemm(p16, e["dyn_w"], e["dyn_b"])
+            return p32, p16
 
         # (running the ROI gather on a parallel stream branch next to this block was measured: slower)
-        p32, params = attn_and_params()
-        # instance interaction (DynamicConv)
-        f2 = ops.roi_dynconv(lv, boxes, N, params, e["dn1"][0], e["dn1"][1], e["dn2"][0], e["dn2"][1], roi_in=roi)
+        p32, p16 = attn_and_params()
+        # instance interaction (DynamicConv): per-box weights (dynamic_layer, 64 KB per box) then the two bmm + LN
+        ch = int(self.dyn_chunk_frames)
+        if ch > 0 and B > ch:
+            # `ch` frames at a time through ONE reused weight buffer: the generated weights of a chunk are consumed
+            # while they are still in L2 and overwritten there by the next chunk
+            f2 = torch.empty((M, 49 * 256), device=dev, dtype=H)
+            pbuf = torch.empty((ch * N, 2 * 256 * 64), device=dev, dtype=H)
+            for f0 in range(0, B, ch):
+                f1 = min(B, f0 + ch)
+                rows = slice(f0 * N, f1 * N)
+                params = ops.gemm(p16[rows], e["dyn_w"], e["dyn_b"], out=pbuf[:(f1 - f0) * N])
+                sub = ops.Levels([f[f0:f1] for f in lv.feats])
+                ops.roi_dynconv(sub, boxes[f0:f1], N, params, e["dn1"][0], e["dn1"][1], e["dn2"][0], e["dn2"][1],
+                                roi_in=None if roi is None else roi[rows], out=f2[rows])
+        else:
+            params = ops.gemm(p16, e["dyn_w"], e["dyn_b"])
+            f2 = ops.roi_dynconv(lv, boxes, N, params, e["dn1"][0], e["dn1"][1], e["dn2"][0], e["dn2"][1], roi_in=roi)
         part, s = ops.gemm_partials(f2, e["ol_w"], 7)
         o32 = torch.empty((M, 256), device=dev, dtype=F32); o16 = torch.empty((M, 256), device=dev, dtype=H)
         ops.row_post(M, partials=part, splits=s, bias=e["ol_b"], ln1=e["dn3"], relu1=True, resid=p32, ln2=e["n2"],

@@ -115,8 +115,11 @@ def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=N
     p1 = params[:, :16384].float().view(M, 256, 64)
     p2 = params[:, 16384:].float().view(M, 64, 256)
     f = F.relu(F.layer_norm(torch.bmm(roi_in.float(), p1), (64,), g1, b1)).half().float()
-    f = F.relu(F.layer_norm(torch.bmm(f, p2), (256,), g2, b2)).half()
-    return f.reshape(M, 49 * 256)
+    f = F.relu(F.layer_norm(torch.bmm(f, p2), (256,), g2, b2)).half().reshape(M, 49 * 256)
+    if out is not None:
+        out.copy_(f)
+        return out
+    return f
 
 
 def row_post(M, partials=None, splits=1, in_f16=None, bias=None, ln1=None, relu1=False, resid=None, ln2=None, act2=0,

@@ -30,13 +30,16 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-streams", action="store_true")
     ap.add_argument("--frames-per-stream", type=int, default=2)
+    ap.add_argument("--backbone", default="r101", choices=["r101", "swinb"])
     a = ap.parse_args()
     from diffusionvid_b200 import model as pm, synth
     dev = torch.device("cuda", 0)
     blocks = tuple(int(x) for x in a.blocks.split(","))
     hp = dict(bench.HP_BASE, num_proposals=a.proposals, sample_step=a.T, device=str(dev), blocks=blocks)
+    if a.backbone == "swinb":
+        hp.update(swin=dict(embed=128, depths=(2, 2, 18, 2), heads=(4, 8, 16, 32)), infer_batch=4, all_frame_interval=4)
     m = pm.DiffusionDet(hp)
-    m.load_state_dict(synth.make_state_dict(seed=1234, blocks=blocks), strict=False)
+    m.load_state_dict(synth.make_state_dict(seed=1234, blocks=blocks, swin=hp.get("swin")), strict=False)
     m.to(dev)
     m.use_graphs = not a.no_graphs
     m.use_streams = not a.no_streams
