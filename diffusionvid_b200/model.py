@@ -107,6 +107,15 @@ class DiffusionDet(nn.Module):
         import os as _os
         self.extract_batch = int(_os.environ.get("DVID_EXTRACT_BATCH", hp.get("extract_batch", 32)))
         self.dyn_chunk_frames = int(_os.environ.get("DVID_DYN_CHUNK", hp.get("dyn_chunk_frames", 0)))
+        # frames that arrive in HOST memory: run the backbone on the frames already uploaded while the later ones are
+        # still crossing PCIe (_extract_pipelined).  Used at a video start (32 frames = 230 MB in one call; chunks of 7
+        # frames = 133 res4 tiles, one wave on 148 SMs): -1.7 ms per clip.  For the steady 8-frame batches
+        # (`pipeline_chunk` frames launched early from the queue-only calls) the smaller backbone units cost as much as
+        # the hidden 0.5 ms of PCIe time: measured equal, left off (0).
+        self.pipeline_uploads = bool(int(_os.environ.get("DVID_PIPELINE", hp.get("pipeline_uploads", 1))))
+        self.pipeline_chunk = int(_os.environ.get("DVID_PIPELINE_CHUNK", hp.get("pipeline_chunk", 0)))
+        self.pipeline_chunk_start = int(_os.environ.get("DVID_PIPELINE_START", hp.get("pipeline_chunk_start", 7)))
+        self._early = None
         self._graphs = {}
         self._streams = []
         self._streams_inner = []
@@ -532,31 +541,39 @@ class DiffusionDet(nn.Module):
     def _extract(self, imgs, box_init, w, h):
         """Backbone + head_series[0..num_heads) at t=999 + top-k memory candidates for B new frames
         (diffusion_det.py:418-460; box_head.py:286-317).  All outputs are per frame."""
+        f = self._features(imgs, w, h)
+        return dict(f, **self._base(f["p3"], f["p4"], f["p5"], box_init, w, h))
+
+    def _features(self, imgs, w, h):
+        """Backbone + FPN of new frames (diffusion_det.py:424-427): NHWC fp16 p3/p4/p5."""
+        outs = self._fork_join([(lambda i0=i0, i1=i1: self.extract_features(imgs[i0:i1]))
+                                for i0, i1 in self._groups(imgs.shape[0])])
+        if len(outs) == 1:
+            return dict(p3=outs[0][0], p4=outs[0][1], p5=outs[0][2])
+        return dict(p3=torch.cat([o[0] for o in outs]), p4=torch.cat([o[1] for o in outs]),
+                    p5=torch.cat([o[2] for o in outs]))
+
+    def _base(self, p3, p4, p5, box_init, w, h):
+        """head_series[0..num_heads) at t=999 on the initial boxes + top-k memory candidates (box_head.py:286-317)."""
         hp = self.hp
         N = self.num_proposals
         k1, k2 = min(hp["topk"][0], N), min(hp["topk"][1], N)
 
         def unit(i0, i1):
             def run():
-                f = self.extract_features(imgs[i0:i1])
-                lv = ops.Levels(f)
+                lv = ops.Levels([p3[i0:i1], p4[i0:i1], p5[i0:i1]])
                 boxes = ops.noise_to_boxes(box_init[i0:i1].contiguous(), hp["snr_scale"], float(w), float(h))
                 lg, bx, o32, o16 = self._base_stages(lv, boxes, 999)
                 m1, m2 = ops.topk_mask(lg, k1, k2)
                 B = i1 - i0
-                return (f, lg, bx, o32.view(B, N, 256), o16.view(B, N, 256),
+                return (lg, bx, o32.view(B, N, 256), o16.view(B, N, 256),
                         ops.gather_masked_rows(o32, m1, k1).view(B, k1, 256),
                         ops.gather_masked_rows(o32, m2, k2).view(B, k2, 256))
             return run
 
-        outs = self._fork_join([unit(i0, i1) for i0, i1 in self._groups(imgs.shape[0])])
-        if len(outs) == 1:
-            f, lg, bx, o32, o16, c1, c2 = outs[0]
-            return dict(p3=f[0], p4=f[1], p5=f[2], lg=lg, bx=bx, o32=o32, o16=o16, k1=c1, k2=c2)
-        cat = lambda i: torch.cat([o[i] for o in outs])
-        return dict(p3=torch.cat([o[0][0] for o in outs]), p4=torch.cat([o[0][1] for o in outs]),
-                    p5=torch.cat([o[0][2] for o in outs]), lg=cat(1), bx=cat(2), o32=cat(3), o16=cat(4), k1=cat(5),
-                    k2=cat(6))
+        outs = self._fork_join([unit(i0, i1) for i0, i1 in self._groups(p3.shape[0])])
+        cat = (lambda i: outs[0][i]) if len(outs) == 1 else (lambda i: torch.cat([o[i] for o in outs]))
+        return dict(lg=cat(0), bx=cat(1), o32=cat(2), o16=cat(3), k1=cat(4), k2=cat(5))
 
     def _ddim_consts(self, t, t_next):
         """float64 scalar math of diffusion_det.py:578-584, rounded to fp32 like the reference's tensors."""
@@ -675,6 +692,7 @@ class DiffusionDet(nn.Module):
         ib = self.infer_batch
         if infos["frame_category"] == 0:
             self.local_img_queue = []
+            self._early = None
             self.proposal_feats_global = [None, None]
             self._mem_kv = None
             self.feats = deque(maxlen=hp["all_frame_interval"])
@@ -688,6 +706,13 @@ class DiffusionDet(nn.Module):
             for il in ref_l:
                 own = len(self.local_img_queue) % world == rank
                 self.local_img_queue.append(self._upload(il, dev) if own else il)
+            q = self.local_img_queue
+            if (self.pipeline_uploads and self.pipeline_chunk > 0 and world == 1 and self._early is None
+                    and len(q) == self.pipeline_chunk and all(isinstance(it, tuple) for it in q)):
+                # half of the next key batch has arrived: its backbone pass is queued behind the uploads now and runs
+                # while the remaining frames of the batch are still in flight
+                hh, ww = imgs.image_sizes[0]
+                self._early = (len(q), self._features_of(q, int(ww), int(hh), dev))
             return []
         ref_l = self.local_img_queue + ref_l
         self.local_img_queue = []
@@ -705,6 +730,12 @@ class DiffusionDet(nn.Module):
             mine = [i for i in range(n_total) if i % world == rank]
             pos = {g: j for j, g in enumerate(mine)}
             ex = None
+            early, self._early = self._early, None
+            host_side = lambda it: isinstance(it, tuple) or not it.tensors.is_cuda      # noqa: E731
+            if (self.pipeline_uploads and world == 1 and dev.type == "cuda" and (early or n_total > ib)
+                    and all(host_side(it) for it in all_imgs[(early[0] if early else 0):])):
+                ex = self._extract_pipelined(all_imgs, early, fid, n_total, w, h, dev)
+                mine = []
             if mine:
                 # host images are copied one by one (asynchronously when pinned) and concatenated on the device
                 total = torch.cat([self._on_device(all_imgs[i], dev) for i in mine])
@@ -798,6 +829,39 @@ class DiffusionDet(nn.Module):
             bl.add_field("labels", ol[i, :c].long())
             results.append(bl)
         return results
+
+    # ------------------------------------------------------------------------------------------ upload pipeline
+    def _features_of(self, items, w, h, dev):
+        """Backbone unit over queued frames (waits for their upload events on the compute stream)."""
+        x = torch.cat([self._on_device(it, dev) for it in items])
+        o = self._run_unit("features", self._features, (w, h), dict(imgs=x), dict(w=w, h=h))
+        return {k: v.clone() for k, v in o.items()} if self._graph_active() else o
+
+    def _extract_pipelined(self, all_imgs, early, fid, n_total, w, h, dev):
+        """`_extract` for frames that come from host memory: every upload is issued first (copy stream, arrival order),
+        then the backbone runs chunk by chunk as the chunks land - PCIe time hides behind the previous chunk's compute
+        instead of preceding the whole batch - and the base stages run once over all frames.  Per-frame results are
+        identical to the one-unit path (nothing in the backbone or the heads mixes frames)."""
+        ib = self.infer_batch
+        n0 = early[0] if early else 0
+        rest = [it if isinstance(it, tuple) else self._upload(it, dev) for it in all_imgs[n0:]]
+        csz = max(1, self.pipeline_chunk_start if n_total > ib else (self.pipeline_chunk or ib))
+        feats = [early[1]] if early else []
+        for c0 in range(0, len(rest), csz):
+            feats.append(self._features_of(rest[c0:c0 + csz], w, h, dev))
+        f = {k: (torch.cat([x[k] for x in feats]) if len(feats) > 1 else feats[0][k]) for k in ("p3", "p4", "p5")}
+        inits = [self._randn("init", fid, bi, min(ib, n_total - bi * ib), dev) for bi in range((n_total + ib - 1) // ib)]
+        box_all = torch.cat(inits) if len(inits) > 1 else inits[0]
+        eb = max(ib, int(self.extract_batch))
+        outs = []
+        for i0 in range(0, n_total, eb):
+            sl = slice(i0, min(n_total, i0 + eb))
+            o = self._run_unit("base", self._base, (w, h),
+                               dict(p3=f["p3"][sl], p4=f["p4"][sl], p5=f["p5"][sl], box_init=box_all[sl].contiguous()),
+                               dict(w=w, h=h))
+            outs.append({k: v.clone() for k, v in o.items()} if self._graph_active() else o)
+        base = {k: (torch.cat([o[k] for o in outs]) if len(outs) > 1 else outs[0][k]) for k in outs[0]}
+        return dict(f, **base)
 
     # ------------------------------------------------------------------------------------------ host <-> device
     def _upload(self, il, dev):
