@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libdvid_b200.so")
+LIB_PATH = os.environ.get("DVID_LIB_PATH") or os.path.join(_HERE, "_C", "libdvid_b200.so")   # override: A/B of builds
 
 ERRORS = {1: "DVID_ERR_SHAPE", 2: "DVID_ERR_CUDA", 3: "DVID_ERR_DRIVER", 4: "DVID_ERR_ARG"}
 

@@ -42,13 +42,6 @@ struct ConvGemmParams {
   long long m_total;     // rows of the GEMM view (n_img * h_out * w_out)
   int dbg;               // DVID_DBG experiment bits (timing experiments only; results are wrong when set)
   unsigned long long* trace;   // DVID_TRACE: per-role event log of CTA 0 (debug only), else nullptr
-  // split-K tail (stream-K for the last, partial wave): the `tail_rem` tiles that do not fill a wave are each computed
-  // by `tail_S` CTAs over K slices; fp32 partials go through `tail_ws`, every CTA then reduces + stores 1/S of the
-  // tile's columns.  tail_S == 0: off.
-  int tail_S, tail_rem, tail_main, tail_kb_per;
-  float* tail_ws;        // [tail_rem][tail_S][128][BN] fp32
-  int* tail_cnt;         // [2 * tail_rem], zero on entry, reset to zero by the last CTA of each tile
-  __half* out_ptr;       // raw NHWC output pointer (the tail reduce stores without TMA)
 };
 
 // BSTAT ("B-stationary", K <= 256): the whole [BN x K] weight tile stays resident in smem while the CTA walks a
@@ -57,7 +50,7 @@ struct ConvGemmParams {
 // GEMMs (dynamic_layer 2400x256->32768: 467 MB of operand reads at 128x256 tiles -> ~190 MB).
 constexpr int BSTAT_MAX_KB = 4;   // K <= 256
 // named barriers: 1 = the four epilogue warps; FULL/FREE = epilogue warps <-> TMA store warp, per staging buffer
-constexpr int BAR_FULL0 = 2, BAR_FREE0 = 4;
+constexpr int BAR_FULL0 = 2, BAR_FREE0 = 4, BAR_BIAS0 = 6;
 
 // RES (residual with resid_shift == 0): the residual tile is ADDED BY THE TENSOR CORE.  Each 64-channel chunk of the
 // residual (same 128-pixel patch as the output tile) is TMA-loaded into an A-ring stage like an extra k-block and
@@ -75,7 +68,8 @@ struct ConvGemmCfg {
   static constexpr int RING_BYTES =
       BSTAT ? (STAGES * A_STAGE_BYTES + BSTAT_MAX_KB * B_STAGE_BYTES) : (STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
   static constexpr int SMEM_BYTES = RING_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                                    BN * 4 /*bias staging*/ + (RES ? IDENT_BYTES : 0);
+                                    (BN * 4 > 512 ? BN * 4 : 512) /*bias staging: each epilogue group its own half*/ +
+                                    (RES ? IDENT_BYTES : 0);
 };
 
 // GELU, erf form (torch.nn.GELU default; Swin MLP, swintransformer.py:47-66): x * Phi(x).  erff() costs ~30
@@ -179,38 +173,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // tile walk: normal = strided over the grid, n fastest; BSTAT = one contiguous range per CTA, m fastest (splits == 1)
   const int tile_begin = BSTAT ? static_cast<int>(static_cast<long long>(total_tiles) * blockIdx.x / gridDim.x)
                                : static_cast<int>(blockIdx.x);
-  const bool has_tail = !BSTAT && p.tail_S > 0;
   const int tile_end = BSTAT ? static_cast<int>(static_cast<long long>(total_tiles) * (blockIdx.x + 1) / gridDim.x)
-                             : (has_tail ? p.tail_main + p.tail_rem * p.tail_S : total_tiles);
+                             : total_tiles;
   const int tile_step = BSTAT ? 1 : static_cast<int>(gridDim.x);
-  // split < 0 encodes a K slice of a tail tile: slice = -1 - split (virtual tiles >= tail_main, see ConvGemmParams)
   auto decode = [&](int tile, int& n_idx, int& m_idx, int& split) {
     if (BSTAT) {
       n_idx = tile / p.m_tiles;
       m_idx = tile - n_idx * p.m_tiles;
       split = 0;
     } else {
-      int t = tile;
-      int slice = -1;
-      if (has_tail && tile >= p.tail_main) {
-        const int item = tile - p.tail_main;
-        slice = item % p.tail_S;
-        t = p.tail_main + item / p.tail_S;
-      }
-      n_idx = t % p.n_tiles;
-      const int rest = t / p.n_tiles;
+      n_idx = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
       m_idx = rest % p.m_tiles;
-      split = slice >= 0 ? (-1 - slice) : rest / p.m_tiles;
+      split = rest / p.m_tiles;
     }
   };
   auto k_range = [&](int split, int& kb_begin, int& kb_end) {
-    if (split < 0) {
-      kb_begin = (-1 - split) * p.tail_kb_per;
-      kb_end = min(p.total_kb, kb_begin + p.tail_kb_per);
-    } else {
-      kb_begin = split * p.kb_per_split;
-      kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
-    }
+    kb_begin = split * p.kb_per_split;
+    kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
   };
 
   if (warp == 0) {
@@ -341,19 +321,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-  } else if (warp == 3) {
-    // ===================== TMA store warp =====================
-    // Takes the staged 128x64 fp16 chunks from the epilogue warps (named barriers FULL0/1) and issues the TMA stores, so
-    // the store issue + the wait for the staging buffer to drain are off the epilogue's critical path.
+  } else if (warp == 2 || warp == 3) {
+    // ===================== TMA store warps =====================
+    // One per epilogue group (warp 2 <-> group 0, warp 3 <-> group 1).  Each takes the staged 128x64 fp16 chunks of ITS
+    // group (named barrier FULL<g>), issues the TMA store, waits until the store has read the staging buffer and hands
+    // the buffer back (FREE<g>).  The two groups therefore never wait for each other: the first version had one store
+    // warp that freed a buffer only after the OTHER group's next chunk had been issued, which serialised the groups
+    // (device trace: 0.6 us per chunk spent waiting for the buffer, profiles/README.md).
     if (p.out_f32 == nullptr && !(p.dbg & 128)) {
-      int total_chunks = 0;
+      const int sg = warp - 2;
+      int mine = 0, gb = 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int n_idx, m_idx, split;
         decode(tile, n_idx, m_idx, split);
-        if (split < 0) continue;            // tail slices store their share themselves
-        total_chunks += min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
+        const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
+        const int cf = (gb + sg) & 1;
+        if (cf < nchunks) mine += (nchunks - cf + 1) / 2;
+        gb += nchunks;
       }
-      int g = 0;
+      int done = 0;
+      gb = 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int n_idx, m_idx, split;
         decode(tile, n_idx, m_idx, split);
@@ -362,20 +349,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int img = m_idx / (p.tiles_x * p.tiles_y);
         const int x0 = tx * tw, y0 = ty * p.th;
         const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
-        if (split < 0) continue;
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const int sb = g & 1;
-          named_bar_sync(BAR_FULL0 + sb, 160);
+        for (int c = (gb + sg) & 1; c < nchunks; c += 2) {
+          named_bar_sync(BAR_FULL0 + sg, 160);
           if (lane == 0 && !(p.dbg & 1)) {
-            tma_store_4d(&tmC, sOut + sb * OUT_STAGE_BYTES, n_idx * BN + c * 64, x0, y0, img);
+            tma_store_4d(&tmC, sOut + sg * OUT_STAGE_BYTES, n_idx * BN + c * 64, x0, y0, img);
             tma_store_commit();
           }
-          if (g >= 1 && g + 1 < total_chunks) {     // chunk g+1 will reuse the buffer of chunk g-1
-            if (lane == 0) tma_store_wait_read<1>();
+          if (++done < mine) {                    // the group will stage another chunk into this buffer
+            if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
-            named_bar_arrive(BAR_FREE0 + (sb ^ 1), 160);
+            named_bar_arrive(BAR_FREE0 + sg, 160);
           }
         }
+        gb += nchunks;
       }
       if (lane == 0) tma_store_wait<0>();
     }
@@ -397,14 +383,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     int tn = 0;
+    const int gt = et & 127;                   // thread index inside the group
+    int staged = 0;                            // chunks this group has handed to its store warp
+    // bias of the group's chunks of a tile: thread gt holds column (gt & 63) of the group's (gt >> 6)-th chunk
     float bnext = 0.f;
-    auto fetch_bias = [&](int tile) {
+    auto fetch_bias = [&](int tile, int gb) {
       int bn_idx, bm_idx, bsplit;
       decode(tile, bn_idx, bm_idx, bsplit);
-      const int col = bn_idx * BN + et;
-      bnext = (p.bias != nullptr && et < BN && col < p.cout) ? __ldg(p.bias + col) : 0.f;
+      const int c = ((gb + grp) & 1) + 2 * (gt >> 6);
+      const int col = bn_idx * BN + c * 64 + (gt & 63);
+      bnext = (p.bias != nullptr && c * 64 < BN && col < p.cout) ? __ldg(p.bias + col) : 0.f;
     };
-    if (tile_begin < tile_end && p.out_f32 == nullptr) fetch_bias(tile_begin);
+    if (tile_begin < tile_end && p.out_f32 == nullptr) fetch_bias(tile_begin, 0);
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       int n_idx, m_idx, split;
       decode(tile, n_idx, m_idx, split);
@@ -442,92 +432,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       if (p.dbg & 128) {
         // experiment: no epilogue work at all (mainloop speed)
-      } else if (split < 0) {
-        // ---- K slice of a tail tile: fp32 partial -> workspace, then reduce + store 1/S of the tile's columns
-        const int S = p.tail_S;
-        const int slice = -1 - split;
-        const int tile_r = (tile - p.tail_main) / S;
-        // workspace layout [tile][slice][32-column piece][row][32]: a warp's dump of one piece is 4 KB contiguous
-        float* wtile = p.tail_ws + static_cast<size_t>(tile_r) * S * BLOCK_M * BN;
-        float* wmine = wtile + static_cast<size_t>(slice) * BLOCK_M * BN + static_cast<size_t>(row) * 32;
-#pragma unroll 1
-        for (int c = grp; c < BN / 32; c += 2) {
-          uint32_t v[32];
-          tmem_ld32(tbase + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(wmine + static_cast<size_t>(c) * BLOCK_M * 32 + q * 4) =
-                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                            __uint_as_float(v[4 * q + 3]));
-        }
-        __threadfence();
-        named_bar_sync(1, 256);
-        if (et == 0) {
-          atomicAdd(p.tail_cnt + tile_r, 1);
-          unsigned spins = 0;
-          while (*reinterpret_cast<volatile int*>(p.tail_cnt + tile_r) < S) {
-            __nanosleep(64);
-            if (++spins > (1u << 24)) {
-              printf("dvid: split-K tail wait timed out (block %d)\n", (int)blockIdx.x);
-              __trap();
-            }
-          }
-        }
-        named_bar_sync(1, 256);
-        __threadfence();
-        {
-          const int cs = BN / S;                 // this CTA's share of the columns
-          const int per = cs / 2;                // two threads per row
-          const int r2 = et & 127, half = et >> 7;
-          const int xx = x0 + (r2 & (tw - 1)), yy = y0 + (r2 >> p.tw_log2);
-          if (xx < p.w_out && yy < p.h_out) {
-            const int col0 = slice * cs + half * per;
-            __half* orow = p.out_ptr + ((static_cast<long long>(img) * p.h_out + yy) * p.w_out + xx) * p.cout +
-                           n_idx * BN + col0;
-#pragma unroll 1
-            for (int j = 0; j < per; j += 8) {
-              if (n_idx * BN + col0 + j >= p.cout) break;
-              const int col = col0 + j;              // 8 consecutive columns inside one 32-column piece
-              const float* src = wtile + (static_cast<size_t>(col >> 5) * BLOCK_M + r2) * 32 + (col & 31);
-              float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              float4 u0[8], u1[8];
-#pragma unroll
-              for (int sidx = 0; sidx < 8; ++sidx) {   // all slices' loads in flight before the first add
-                if (sidx < S) {
-                  u0[sidx] = *reinterpret_cast<const float4*>(src + static_cast<size_t>(sidx) * BLOCK_M * BN);
-                  u1[sidx] = *reinterpret_cast<const float4*>(src + static_cast<size_t>(sidx) * BLOCK_M * BN + 4);
-                }
-              }
-#pragma unroll
-              for (int sidx = 0; sidx < 8; ++sidx) {
-                if (sidx < S) {
-                  a8[0] += u0[sidx].x; a8[1] += u0[sidx].y; a8[2] += u0[sidx].z; a8[3] += u0[sidx].w;
-                  a8[4] += u1[sidx].x; a8[5] += u1[sidx].y; a8[6] += u1[sidx].z; a8[7] += u1[sidx].w;
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                if (p.bias != nullptr) a8[e] += __ldg(p.bias + n_idx * BN + col0 + j + e);
-                if (p.relu == 1) a8[e] = fmaxf(a8[e], 0.f);
-                else if (p.relu == 2) a8[e] = gelu_erf(a8[e]);
-              }
-              uint4 pk;
-              pk.x = pack_half2(a8[0], a8[1]); pk.y = pack_half2(a8[2], a8[3]);
-              pk.z = pack_half2(a8[4], a8[5]); pk.w = pack_half2(a8[6], a8[7]);
-              *reinterpret_cast<uint4*>(orow + j) = pk;
-            }
-          }
-        }
-        named_bar_sync(1, 256);
-        if (et == 0) {                           // the last CTA of the tile re-arms the counters for the next launch
-          const int old = atomicAdd(p.tail_cnt + p.tail_rem + tile_r, 1);
-          if (old == S - 1) {
-            p.tail_cnt[tile_r] = 0;
-            p.tail_cnt[p.tail_rem + tile_r] = 0;
-            __threadfence();
-          }
-        }
       } else if (p.out_f32 != nullptr) {
         // split-K partials: fp32, direct vector stores (GEMM view: th == 1, row index = x); 32-column pieces
         // alternate between the two groups
@@ -553,10 +457,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         // stage this tile's bias: the first barrier orders the previous tile's last sBias reads before these writes,
         // the second these writes before this tile's reads.  Then start fetching the next tile's bias.
-        named_bar_sync(1, 256);
-        if (et < BN) sBias[et] = bnext;
-        if (tile + tile_step < tile_end) fetch_bias(tile + tile_step);
-        named_bar_sync(1, 256);
+        float* gBias = sBias + grp * (BN > 128 ? BN / 2 : 64);   // each group stages its own chunks' bias: no barrier
+        named_bar_sync(BAR_BIAS0 + grp, 128);                    // across the groups
+        if (gt < (BN > 128 ? BN / 2 : 64)) gBias[gt] = bnext;
+        if (tile + tile_step < tile_end) fetch_bias(tile + tile_step, gbase + nchunks);
+        named_bar_sync(BAR_BIAS0 + grp, 128);
         uint8_t* buf = sOut + grp * OUT_STAGE_BYTES;
 #pragma unroll 1
         for (int c = c_first; c < nchunks; c += 2) {
@@ -570,14 +475,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tmem_ld32(tbase + c * 64, v[0]);
           tmem_ld32(tbase + c * 64 + 32, v[1]);
           // the store warp has drained the TMA store that last read this group's staging buffer
-          if (gbase + c >= 2) named_bar_sync(BAR_FREE0 + grp, 160);
+          if (staged > 0) named_bar_sync(BAR_FREE0 + grp, 160);
           tmem_ld_wait();
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(sBias + c * 64 + h * 32 + j);
+              const float4 b4 = *reinterpret_cast<const float4*>(gBias + ((c - c_first) >> 1) * 64 + h * 32 + j);
               f[j] = __uint_as_float(v[h][j]) + b4.x;
               f[j + 1] = __uint_as_float(v[h][j + 1]) + b4.y;
               f[j + 2] = __uint_as_float(v[h][j + 2]) + b4.z;
@@ -614,6 +519,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           fence_proxy_async_smem();
           named_bar_arrive(BAR_FULL0 + grp, 160);   // hand the staged chunk to the store warp, do not wait for it
+          ++staged;
           if (et == 0) trace_ev(p, 2, tn, (tile << 8) | c);
         }
         gbase += nchunks;
@@ -730,7 +636,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     const char* names[3] = {"load", "mma ", "epi "};
     for (int r = 0; r < 3; ++r)
       for (int i = 0; i < 1023 && host[r * 2048 + 2 * i + 1]; ++i) {
-        if (i > 60) break;
+        if (i > 120) break;
         fprintf(stderr, "  %s tile %4llu ev %3llu  t=%8.2f us\n", names[r], host[r * 2048 + 2 * i] >> 8,
                 host[r * 2048 + 2 * i] & 0xff, (host[r * 2048 + 2 * i + 1] - t0) / 1900.0);
       }
@@ -745,6 +651,7 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
                      float* out_f32, int n, int h, int w, int cin, int cout, int R, int S, int stride, int pad,
                      int resid_shift, int relu, int splits, int force_bn, cudaStream_t stream,
                      const uint64_t* a_strides_bytes, void* workspace, size_t workspace_bytes) {
+  (void)workspace; (void)workspace_bytes;   // reserved (a split-K tail for partial waves used it; measured slower, removed)
   if (cin % 8 != 0 || cout % 8 != 0) return DVID_ERR_SHAPE;
   if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return DVID_ERR_SHAPE;
   if (stride < 1 || stride > 2) return DVID_ERR_SHAPE;
@@ -865,32 +772,6 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   if (bstat_env < 0) { const char* e = getenv("DVID_BSTAT"); bstat_env = e ? atoi(e) : 1; }
   const bool bstat = bstat_env && out_f32 == nullptr && p.total_kb <= BSTAT_MAX_KB && bn >= 128 &&
                      static_cast<long long>(p.m_tiles) * p.n_tiles >= 2LL * num_sms();
-  // split-K tail: when the tiles are a little more than a whole number of waves, the left-over tiles would cost a full
-  // extra wave on a handful of SMs (res4: 152 tiles on 148 SMs = 2 waves).  Split each of them over K instead.
-  p.tail_S = 0; p.tail_rem = 0; p.tail_main = 0; p.tail_kb_per = 0; p.tail_ws = nullptr; p.tail_cnt = nullptr;
-  p.out_ptr = static_cast<__half*>(out);
-  {
-    static int tail_env = -1;
-    if (tail_env < 0) { const char* e = getenv("DVID_TAIL"); tail_env = e ? atoi(e) : 1; }
-    const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
-    const int G = num_sms();
-    if (tail_env && !bstat && out != nullptr && out_f32 == nullptr && resid == nullptr && workspace != nullptr &&
-        tiles > G && tiles % G != 0 && (tiles % G) * 4 <= G && p.total_kb >= 8 && bn >= 128) {
-      const int rem = static_cast<int>(tiles % G);
-      int S = 8;
-      while (S > 1 && (rem * S > G || p.total_kb / S < 2)) S >>= 1;
-      if (S >= 2) {
-        const int kb_per = (p.total_kb + S - 1) / S;
-        S = (p.total_kb + kb_per - 1) / kb_per;
-        const size_t need = 256 + static_cast<size_t>(rem) * S * BLOCK_M * bn * sizeof(float);
-        if ((S == 2 || S == 4 || S == 8) && need <= workspace_bytes && 2 * rem * sizeof(int) <= 256) {
-          p.tail_S = S; p.tail_rem = rem; p.tail_main = static_cast<int>(tiles - rem); p.tail_kb_per = kb_per;
-          p.tail_cnt = static_cast<int*>(workspace);
-          p.tail_ws = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 256);
-        }
-      }
-    }
-  }
   // residual through the tensor core (identity MMA) whenever it is a same-resolution tensor and the tile is >= 128 wide
   const bool res_mma = resid != nullptr && resid_shift == 0 && out != nullptr && bn >= 128;
   CUtensorMap tmR = tmC;

@@ -115,7 +115,9 @@ class DiffusionDet(nn.Module):
         self.pipeline_uploads = bool(int(_os.environ.get("DVID_PIPELINE", hp.get("pipeline_uploads", 1))))
         self.pipeline_chunk = int(_os.environ.get("DVID_PIPELINE_CHUNK", hp.get("pipeline_chunk", 0)))
         self.pipeline_chunk_start = int(_os.environ.get("DVID_PIPELINE_START", hp.get("pipeline_chunk_start", 7)))
+        self.backbone_frames_per_stream = int(_os.environ.get("DVID_BACKBONE_GROUP", hp.get("backbone_frames_per_stream", 0))) or None
         self._early = None
+        self._pipeline_device = bool(int(_os.environ.get("DVID_PIPELINE_DEVICE", "0")))   # experiment switch
         self._graphs = {}
         self._streams = []
         self._streams_inner = []
@@ -532,8 +534,8 @@ class DiffusionDet(nn.Module):
     def _can_fork(self):
         return torch.device(self.device).type == "cuda" and self.use_streams
 
-    def _groups(self, B):
-        g = max(1, int(self.frames_per_stream))
+    def _groups(self, B, g=None):
+        g = max(1, int(self.frames_per_stream if g is None else g))
         if not self.use_streams or torch.device(self.device).type != "cuda":
             g = B
         return [(i, min(B, i + g)) for i in range(0, B, g)]
@@ -547,7 +549,7 @@ class DiffusionDet(nn.Module):
     def _features(self, imgs, w, h):
         """Backbone + FPN of new frames (diffusion_det.py:424-427): NHWC fp16 p3/p4/p5."""
         outs = self._fork_join([(lambda i0=i0, i1=i1: self.extract_features(imgs[i0:i1]))
-                                for i0, i1 in self._groups(imgs.shape[0])])
+                                for i0, i1 in self._groups(imgs.shape[0], self.backbone_frames_per_stream)])
         if len(outs) == 1:
             return dict(p3=outs[0][0], p4=outs[0][1], p5=outs[0][2])
         return dict(p3=torch.cat([o[0] for o in outs]), p4=torch.cat([o[1] for o in outs]),
@@ -733,7 +735,7 @@ class DiffusionDet(nn.Module):
             early, self._early = self._early, None
             host_side = lambda it: isinstance(it, tuple) or not it.tensors.is_cuda      # noqa: E731
             if (self.pipeline_uploads and world == 1 and dev.type == "cuda" and (early or n_total > ib)
-                    and all(host_side(it) for it in all_imgs[(early[0] if early else 0):])):
+                    and (self._pipeline_device or all(host_side(it) for it in all_imgs[(early[0] if early else 0):]))):
                 ex = self._extract_pipelined(all_imgs, early, fid, n_total, w, h, dev)
                 mine = []
             if mine:
