@@ -22,7 +22,7 @@ F = ctypes.c_float
 SIGNATURES = {
     "dvid_abi_version": [],
     "dvid_num_sms": [],
-    "dvid_conv2d_nhwc_f16": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, L, P],
+    "dvid_conv2d_nhwc_f16": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dvid_stem_conv_f16": [P, P, P, P, I, I, I, I, I, P],
     "dvid_gemm_f16": [P, P, P, P, P, P, I, I, I, I, I, P, P],
     "dvid_preprocess": [P, P, I, I, I, I, I, I, P, P, P],

@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 6
+#define DVID_ABI_VERSION 7
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -13,11 +13,10 @@ int dvid_num_sms(void) { return dvid::num_sms(); }
 
 int dvid_conv2d_nhwc_f16(const void* in, const void* weight, const float* bias, const void* resid, void* out, int n,
                          int h, int w, int cin, int cout, int R, int S_, int stride, int pad, int resid_shift,
-                         int relu, void* workspace, long workspace_bytes, void* stream) {
+                         int relu, void* stream) {
   if (!in || !weight || !out) return DVID_ERR_ARG;
   return dvid::conv_gemm_launch(in, weight, bias, resid, out, nullptr, n, h, w, cin, cout, R, S_, stride, pad,
-                                resid_shift, relu, 1, 0, S(stream), nullptr, workspace,
-                                workspace_bytes > 0 ? static_cast<size_t>(workspace_bytes) : 0);
+                                resid_shift, relu, 1, 0, S(stream), nullptr);
 }
 
 int dvid_stem_conv_f16(const void* in_haloed, const void* weight, const float* bias, void* out, int n, int H, int W,

@@ -650,8 +650,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 int conv_gemm_launch(const void* in, const void* weight, const float* bias, const void* resid, void* out,
                      float* out_f32, int n, int h, int w, int cin, int cout, int R, int S, int stride, int pad,
                      int resid_shift, int relu, int splits, int force_bn, cudaStream_t stream,
-                     const uint64_t* a_strides_bytes, void* workspace, size_t workspace_bytes) {
-  (void)workspace; (void)workspace_bytes;   // reserved (a split-K tail for partial waves used it; measured slower, removed)
+                     const uint64_t* a_strides_bytes) {
   if (cin % 8 != 0 || cout % 8 != 0) return DVID_ERR_SHAPE;
   if (n <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0) return DVID_ERR_SHAPE;
   if (stride < 1 || stride > 2) return DVID_ERR_SHAPE;
@@ -812,7 +811,7 @@ int stem_conv_launch(const void* in_haloed, const void* weight, const float* bia
   const uint64_t wp = (uint64_t)W + 6, hp = (uint64_t)H + 6;
   const uint64_t strides[3] = {16, wp * 16, hp * wp * 16};
   return conv_gemm_launch(in_haloed, weight, bias, nullptr, out, nullptr, n, H + 6, W - 1, 64, cout, 7, 1, 2, 0, 0, relu,
-                          1, 0, stream, strides, nullptr, 0);
+                          1, 0, stream, strides);
 }
 
 }  // namespace dvid

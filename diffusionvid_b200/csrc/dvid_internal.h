@@ -21,7 +21,7 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 int conv_gemm_launch(const void* in, const void* weight, const float* bias, const void* resid, void* out,
                      float* out_f32, int n, int h, int w, int cin, int cout, int R, int S, int stride, int pad,
                      int resid_shift, int relu, int splits, int force_bn, cudaStream_t stream,
-                     const uint64_t* a_strides_bytes = nullptr, void* workspace = nullptr, size_t workspace_bytes = 0);
+                     const uint64_t* a_strides_bytes = nullptr);
 int stem_conv_launch(const void* in_haloed, const void* weight, const float* bias, void* out, int n, int H, int W,
                      int cout, int relu, cudaStream_t stream);
 

@@ -67,25 +67,6 @@ def require_device(dev):
 
 
 # ------------------------------------------------------------------------------------------------ dense
-CONV_WS_BYTES = 256 + 36 * 8 * 128 * 256 * 4     # DVID_CONV_WORKSPACE_BYTES
-# The split-K tail of dvid_conv2d_nhwc_f16 is correct (tests/test_gpu_conv_gemm.py) but measured SLOWER than the extra
-# wave it removes on B200 (res4 1x1: 42 us vs 30 us, 3x3: 47 us vs 40 us - the fp32 round trip through L2 plus the
-# inter-CTA hand-shake cost more than 4 left-over tiles), so the product does not pass a workspace by default.
-CONV_TAIL = False
-_conv_ws = {}
-
-
-def _conv_workspace(dev):
-    """Split-K tail workspace, one per (device, stream): zeroed once, the kernel re-arms its counters itself."""
-    key = (dev.index, torch.cuda.current_stream().cuda_stream)
-    ws = _conv_ws.get(key)
-    if ws is None:
-        ws = torch.empty((CONV_WS_BYTES,), device=dev, dtype=torch.uint8)
-        ws[:256].zero_()
-        _conv_ws[key] = ws
-    return ws
-
-
 def conv2d(x, w, bias, cout, R, S, stride, pad, relu, resid=None, resid_shift=0, out=None):
     """x NHWC fp16, w [cout][R*S*cin] fp16 -> NHWC fp16."""
     _chk(x, H, "x"); _chk(w, H, "w"); _chk(bias, F32, "bias"); _chk(resid, H, "resid")
@@ -97,10 +78,8 @@ def conv2d(x, w, bias, cout, R, S, stride, pad, relu, resid=None, resid_shift=0,
     with _prof("conv_gemm", 2.0 * n * ho * wo * cout * R * S * cin,
                2.0 * (x.numel() + w.numel() + n * ho * wo * cout * (2 if resid is not None else 1)),
                tag="conv %dx%d s%d %d->%d @%dx%dx%d%s" % (R, S, stride, cin, cout, n, ho, wo, "+res" if resid is not None else "")):
-        ws = _conv_workspace(x.device) if CONV_TAIL else None
         check(_lib.lib().dvid_conv2d_nhwc_f16(ptr(x), ptr(w), ptr(bias), ptr(resid), ptr(out), n, h, wd, cin, cout, R,
-                                              S, stride, pad, resid_shift, int(relu), ptr(ws),
-                                              CONV_WS_BYTES if ws is not None else 0, cur_stream()),
+                                              S, stride, pad, resid_shift, int(relu), cur_stream()),
               "dvid_conv2d_nhwc_f16")
     _cnt()
     return out

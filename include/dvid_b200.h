@@ -48,14 +48,10 @@ DVID_API int dvid_num_sms(void);
  * resid_shift=1 implements FPN's nearest x2 top-down addition. bias/resid may be NULL.
  * relu: activation 0 none / 1 ReLU / 2 GELU(erf) (same meaning in dvid_gemm_f16).
  * Requirements: Cin % 8 == 0, Cout % 8 == 0, stride in {1,2}.
- * workspace (optional, device, DVID_CONV_WORKSPACE_BYTES, its first 256 bytes ZERO before the first use and owned by
- * one stream at a time): lets the kernel split the tiles of a partial last wave over K (fp32 partials + in-kernel
- * reduction); results do not depend on whether it is given beyond fp32 summation order.
  */
-#define DVID_CONV_WORKSPACE_BYTES (256 + 36 * 8 * 128 * 256 * 4)
 DVID_API int dvid_conv2d_nhwc_f16(const void* in, const void* weight, const float* bias, const void* resid, void* out,
                          int n, int h, int w, int cin, int cout, int R, int S, int stride, int pad,
-                         int resid_shift, int relu, void* workspace, long workspace_bytes, void* stream);
+                         int resid_shift, int relu, void* stream);
 
 /* Stem: 7x7 / stride 2 / pad 3 convolution of the 3-channel image (detectron2 BasicStem) + ReLU.
  * `in_haloed`: output of dvid_preprocess with halo 3: [n][H+6][W+6][8] fp16.  `weight`: [cout][7][8][8] fp16 with
