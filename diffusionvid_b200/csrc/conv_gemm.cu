@@ -385,6 +385,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int tn = 0;
     const int gt = et & 127;                   // thread index inside the group
     int staged = 0;                            // chunks this group has handed to its store warp
+    int staged_key = -1;                       // (n_idx, first chunk) whose bias is in the group's smem stage
     // bias of the group's chunks of a tile: thread gt holds column (gt & 63) of the group's (gt >> 6)-th chunk
     float bnext = 0.f;
     auto fetch_bias = [&](int tile, int gb) {
@@ -458,10 +459,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // stage this tile's bias: the first barrier orders the previous tile's last sBias reads before these writes,
         // the second these writes before this tile's reads.  Then start fetching the next tile's bias.
         float* gBias = sBias + grp * (BN > 128 ? BN / 2 : 64);   // each group stages its own chunks' bias: no barrier
-        named_bar_sync(BAR_BIAS0 + grp, 128);                    // across the groups
-        if (gt < (BN > 128 ? BN / 2 : 64)) gBias[gt] = bnext;
+        const int bias_key = n_idx * 2 + c_first;                // across the groups
+        if (bias_key != staged_key) {      // the weight-stationary walk keeps n_idx for many tiles: stage once
+          named_bar_sync(BAR_BIAS0 + grp, 128);
+          if (gt < (BN > 128 ? BN / 2 : 64)) gBias[gt] = bnext;
+          named_bar_sync(BAR_BIAS0 + grp, 128);
+          staged_key = bias_key;
+        }
         if (tile + tile_step < tile_end) fetch_bias(tile + tile_step, gbase + nchunks);
-        named_bar_sync(BAR_BIAS0 + grp, 128);
         uint8_t* buf = sOut + grp * OUT_STAGE_BYTES;
 #pragma unroll 1
         for (int c = c_first; c < nchunks; c += 2) {
