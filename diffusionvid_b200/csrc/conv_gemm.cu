@@ -23,6 +23,27 @@ constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int OUT_STAGE_BYTES = BLOCK_M * 64 * 2;     // 16 KB, two of them (ping-pong)
 
+// n / d for 0 <= n < 2^31 and a divisor fixed on the host: q = umulhi(n, mul) >> shr  (d == 1: q = n)
+struct FastDiv {
+  unsigned d, mul, shr;
+  __host__ void init(int denom) {
+    d = static_cast<unsigned>(denom < 1 ? 1 : denom);
+    if (d == 1) { mul = 0; shr = 0; return; }
+    unsigned lg = 0;
+    while ((1ull << lg) < d) ++lg;                 // ceil(log2(d))
+    const unsigned pw = 31 + lg;
+    mul = static_cast<unsigned>(((1ull << pw) + d - 1) / d);
+    shr = pw - 32;
+  }
+  __device__ __forceinline__ int div(int n) const {
+    return d == 1 ? n : static_cast<int>(__umulhi(static_cast<unsigned>(n), mul) >> shr);
+  }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+    q = div(n);
+    r = n - q * static_cast<int>(d);
+  }
+};
+
 struct ConvGemmParams {
   int n_img, h_out, w_out;
   int cin, cout;
@@ -41,6 +62,10 @@ struct ConvGemmParams {
   float* out_f32;        // if set: fp32 output [splits][M][cout] by direct stores (GEMM mode), no bias/resid/relu
   long long m_total;     // rows of the GEMM view (n_img * h_out * w_out)
   int dbg;               // DVID_DBG experiment bits (timing experiments only; results are wrong when set)
+  // division by the (launch-invariant) tile counts as multiply-high + shift: every role decodes its tile index once per
+  // tile and a 32-bit integer division is a ~35-instruction dependent chain - five of them cost the epilogue ~0.4 us
+  // per tile (device trace), as much as converting a 64-column chunk
+  FastDiv div_m_tiles, div_n_tiles, div_tiles_x, div_tiles_y;
   unsigned long long* trace;   // DVID_TRACE: per-role event log of CTA 0 (debug only), else nullptr
 };
 
@@ -178,15 +203,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tile_step = BSTAT ? 1 : static_cast<int>(gridDim.x);
   auto decode = [&](int tile, int& n_idx, int& m_idx, int& split) {
     if (BSTAT) {
-      n_idx = tile / p.m_tiles;
-      m_idx = tile - n_idx * p.m_tiles;
+      p.div_m_tiles.divmod(tile, n_idx, m_idx);
       split = 0;
     } else {
-      n_idx = tile % p.n_tiles;
-      const int rest = tile / p.n_tiles;
-      m_idx = rest % p.m_tiles;
-      split = rest / p.m_tiles;
+      int rest;
+      p.div_n_tiles.divmod(tile, rest, n_idx);
+      p.div_m_tiles.divmod(rest, split, m_idx);
     }
+  };
+  // m tile -> (x tile, y tile, image)
+  auto locate = [&](int m_idx, int& tx, int& ty, int& img) {
+    int rest;
+    p.div_tiles_x.divmod(m_idx, rest, tx);
+    p.div_tiles_y.divmod(rest, img, ty);
   };
   auto k_range = [&](int split, int& kb_begin, int& kb_end) {
     kb_begin = split * p.kb_per_split;
@@ -204,9 +233,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int n_idx, m_idx, split;
         decode(tile, n_idx, m_idx, split);
-        const int tx = m_idx % p.tiles_x;
-        const int ty = (m_idx / p.tiles_x) % p.tiles_y;
-        const int img = m_idx / (p.tiles_x * p.tiles_y);
+        int tx, ty, img;
+        locate(m_idx, tx, ty, img);
         const int x_in0 = tx * tw * p.stride - p.pad;
         const int y_in0 = ty * p.th * p.stride - p.pad;
         int kb_begin, kb_end;
@@ -273,7 +301,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       bool last_of_n = false;
       if (BSTAT) {
         const int nt = tile + tile_step;
-        last_of_n = (nt < tile_end) && (nt / p.m_tiles != n_idx);
+        last_of_n = (nt < tile_end) && (p.div_m_tiles.div(nt) != n_idx);
       }
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tc_fence_after();
@@ -344,9 +372,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         int n_idx, m_idx, split;
         decode(tile, n_idx, m_idx, split);
-        const int tx = m_idx % p.tiles_x;
-        const int ty = (m_idx / p.tiles_x) % p.tiles_y;
-        const int img = m_idx / (p.tiles_x * p.tiles_y);
+        int tx, ty, img;
+        locate(m_idx, tx, ty, img);
         const int x0 = tx * tw, y0 = ty * p.th;
         const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
         for (int c = (gb + sg) & 1; c < nchunks; c += 2) {
@@ -399,9 +426,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       int n_idx, m_idx, split;
       decode(tile, n_idx, m_idx, split);
-      const int tx = m_idx % p.tiles_x;
-      const int ty = (m_idx / p.tiles_x) % p.tiles_y;
-      const int img = m_idx / (p.tiles_x * p.tiles_y);
+      int tx, ty, img;
+      locate(m_idx, tx, ty, img);
       const int x0 = tx * tw, y0 = ty * p.th;
       const int x = x0 + (row & (tw - 1));
       const int y = y0 + (row >> p.tw_log2);
@@ -739,6 +765,10 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   }
   if (bn != 64 && bn != 128 && bn != 256) return DVID_ERR_SHAPE;
   p.n_tiles = (cout + bn - 1) / bn;
+  p.div_m_tiles.init(p.m_tiles);
+  p.div_n_tiles.init(p.n_tiles);
+  p.div_tiles_x.init(p.tiles_x);
+  p.div_tiles_y.init(p.tiles_y);
 
   CUtensorMap tmA, tmB, tmC;
   {
