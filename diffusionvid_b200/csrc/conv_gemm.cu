@@ -246,17 +246,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           cur_n = n_idx;
           mbar_expect_tx(bres_full, p.total_kb * Cfg::B_STAGE_BYTES);
-          for (int kb = 0; kb < p.total_kb; ++kb) {
-            const int tap = kb / p.kb_per_tap;
-            const int cblk = kb - tap * p.kb_per_tap;
+          for (int kb = 0, tap = 0, cblk = 0; kb < p.total_kb; ++kb) {
             tma_load_2d(sB + kb * Cfg::B_STAGE_BYTES, &tmB, bres_full, tap * p.cin + cblk * BLOCK_K, n_idx * BN);
+            if (++cblk == p.kb_per_tap) { cblk = 0; ++tap; }
           }
         }
+        // (tap, channel block, filter row, filter column) of the k-block, advanced incrementally: the divisions
+        // they replace were a dependent ~70-instruction chain per k-block on the single producer thread
+        int tap = 0, cblk = 0, r = 0, s = 0;
+        if (kb_begin != 0) {                       // split-K slices only
+          tap = kb_begin / p.kb_per_tap;
+          cblk = kb_begin - tap * p.kb_per_tap;
+          r = tap / p.S;
+          s = tap - r * p.S;
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          const int tap = kb / p.kb_per_tap;
-          const int cblk = kb - tap * p.kb_per_tap;
-          const int r = tap / p.S;
-          const int s = tap - r * p.S;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           trace_ev(p, 0, tn, (tile << 8) | kb);     // slot free, load issued
           mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (BSTAT ? 0 : Cfg::B_STAGE_BYTES));
@@ -265,6 +269,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], tap * p.cin + cblk * BLOCK_K,
                         n_idx * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++cblk == p.kb_per_tap) {
+            cblk = 0;
+            ++tap;
+            if (++s == p.S) { s = 0; ++r; }
+          }
         }
         if (RES) {
           const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
