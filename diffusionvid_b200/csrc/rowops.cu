@@ -15,60 +15,55 @@ namespace {
 __global__ void preprocess_kernel(const float* __restrict__ img, __half* __restrict__ out, int n, int H, int W, int halo,
                                   int Hp, int Wp, float m0, float m1, float m2, float s0, float s1, float s2) {
   pdl_prologue();
-  const long total = static_cast<long>(n) * Hp * Wp;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int xp = static_cast<int>(i % Wp);
-    const int yp = static_cast<int>((i / Wp) % Hp);
-    const int im = static_cast<int>(i / (static_cast<long>(Wp) * Hp));
-    const int x = xp - halo, y = yp - halo;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (x >= 0 && x < W && y >= 0 && y < H) {
-      const long plane = static_cast<long>(H) * W;
-      const float* p = img + static_cast<long>(im) * 3 * plane + static_cast<long>(y) * W + x;
-      const float r = __fdiv_rn(__fsub_rn(__ldg(p), m0), s0);
-      const float g = __fdiv_rn(__fsub_rn(__ldg(p + plane), m1), s1);
-      const float b = __fdiv_rn(__fsub_rn(__ldg(p + 2 * plane), m2), s2);
-      v.x = pack2h(r, g);
-      v.y = pack2h(b, 0.f);
-    }
-    *reinterpret_cast<uint4*>(out + i * 8) = v;
+  // grid (x blocks, padded row, image): no index arithmetic beyond adds (the first version decoded a flat 64-bit index
+  // with three 64-bit divisions per pixel and was instruction-bound at 2.3x its HBM time)
+  const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xp >= Wp) return;
+  const int yp = blockIdx.y, im = blockIdx.z;
+  const int x = xp - halo, y = yp - halo;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (x >= 0 && x < W && y >= 0 && y < H) {
+    const long plane = static_cast<long>(H) * W;
+    const float* p = img + static_cast<long>(im) * 3 * plane + static_cast<long>(y) * W + x;
+    const float r = __fdiv_rn(__fsub_rn(__ldg(p), m0), s0);
+    const float g = __fdiv_rn(__fsub_rn(__ldg(p + plane), m1), s1);
+    const float b = __fdiv_rn(__fsub_rn(__ldg(p + 2 * plane), m2), s2);
+    v.x = pack2h(r, g);
+    v.y = pack2h(b, 0.f);
   }
+  *reinterpret_cast<uint4*>(out + ((static_cast<long>(im) * Hp + yp) * Wp + xp) * 8) = v;
 }
 
 // ------------------------------------------------------------------------------------------------ maxpool 3x3 s2 p1
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n, int H, int W, int C,
                                     int Ho, int Wo) {
   pdl_prologue();
+  // grid (blocks over (x, 8-channel group), output row, image)
   const int cg = C / 8;
-  const long total = static_cast<long>(n) * Ho * Wo * cg;
-  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cg);
-    const int xo = static_cast<int>((i / cg) % Wo);
-    const int yo = static_cast<int>((i / (static_cast<long>(cg) * Wo)) % Ho);
-    const int im = static_cast<int>(i / (static_cast<long>(cg) * Wo * Ho));
-    __half2 m[4];
-    const __half2 ninf = __float2half2_rn(-65504.f);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Wo * cg) return;
+  const int xo = idx / cg, c = idx - xo * cg;
+  const int yo = blockIdx.y, im = blockIdx.z;
+  __half2 m[4];
+  const __half2 ninf = __float2half2_rn(-65504.f);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) m[e] = ninf;
+  for (int e = 0; e < 4; ++e) m[e] = ninf;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int y = yo * 2 - 1 + dy;
-      if (y < 0 || y >= H) continue;
+  for (int dy = 0; dy < 3; ++dy) {
+    const int y = yo * 2 - 1 + dy;
+    if (y < 0 || y >= H) continue;
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int x = xo * 2 - 1 + dx;
-        if (x < 0 || x >= W) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long>(im) * H + y) * W + x) * C + c * 8));
-        const __half2* hp = reinterpret_cast<const __half2*>(&v);
+    for (int dx = 0; dx < 3; ++dx) {
+      const int x = xo * 2 - 1 + dx;
+      if (x < 0 || x >= W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long>(im) * H + y) * W + x) * C + c * 8));
+      const __half2* hp = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], hp[e]);
-      }
+      for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], hp[e]);
     }
-    *reinterpret_cast<uint4*>(out + ((static_cast<long>(im) * Ho + yo) * Wo + xo) * C + c * 8) =
-        *reinterpret_cast<uint4*>(m);
   }
+  *reinterpret_cast<uint4*>(out + ((static_cast<long>(im) * Ho + yo) * Wo + xo) * C + c * 8) =
+      *reinterpret_cast<uint4*>(m);
 }
 
 // ------------------------------------------------------------------------------------------------ row_post (D = 256)
@@ -400,8 +395,8 @@ inline int grid_for(long total, int block) {
 int preprocess_launch(const float* img, void* out, int n, int H, int W, int halo, int Hp, int Wp, const float* mean,
                       const float* std, cudaStream_t stream) {
   if (n <= 0 || H <= 0 || W <= 0 || Hp < H + 2 * halo || Wp < W + 2 * halo) return DVID_ERR_SHAPE;
-  const long total = static_cast<long>(n) * Hp * Wp;
-  launch_pdl(preprocess_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, img, static_cast<__half*>(out), n, H, W, halo, Hp, Wp,
+  if (Hp > 65535 || n > 65535) return DVID_ERR_SHAPE;
+  launch_pdl(preprocess_kernel, dim3((Wp + 255) / 256, Hp, n), dim3(256), 0, stream, img, static_cast<__half*>(out), n, H, W, halo, Hp, Wp,
                                                               mean[0], mean[1], mean[2], std[0], std[1], std[2]);
   return check_launch();
 }
@@ -409,8 +404,8 @@ int preprocess_launch(const float* img, void* out, int n, int H, int W, int halo
 int maxpool_launch(const void* in, void* out, int n, int H, int W, int C, cudaStream_t stream) {
   if (n <= 0 || H <= 0 || W <= 0 || C % 8 != 0) return DVID_ERR_SHAPE;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long total = static_cast<long>(n) * Ho * Wo * (C / 8);
-  launch_pdl(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, static_cast<const __half*>(in),
+  if (Ho > 65535 || n > 65535) return DVID_ERR_SHAPE;
+  launch_pdl(maxpool3x3s2_kernel, dim3((Wo * (C / 8) + 255) / 256, Ho, n), dim3(256), 0, stream, static_cast<const __half*>(in),
                                                                 static_cast<__half*>(out), n, H, W, C, Ho, Wo);
   return check_launch();
 }

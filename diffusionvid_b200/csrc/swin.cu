@@ -27,13 +27,15 @@ struct SwinGeom {
 };
 
 // windowed row -> token (b,y,x); returns false for a zero-pad token
-__device__ __forceinline__ bool win_row_to_token(const SwinGeom& g, long r, int& b, int& y, int& x) {
-  const int t = static_cast<int>(r % WT);
-  long win = r / WT;
-  const int wx = static_cast<int>(win % g.nwx);
+// (row counts stay below 2^31 - checked by the launchers - so all index arithmetic is 32-bit: a 64-bit division by a
+// run-time value is a ~100-instruction sequence and the C = 128 rows were instruction-bound on six of them per row)
+__device__ __forceinline__ bool win_row_to_token(const SwinGeom& g, int r, int& b, int& y, int& x) {
+  const int t = r % WT;
+  int win = r / WT;
+  const int wx = win % g.nwx;
   win /= g.nwx;
-  const int wy = static_cast<int>(win % g.nwy);
-  b = static_cast<int>(win / g.nwy);
+  const int wy = win % g.nwy;
+  b = win / g.nwy;
   int ys = wy * WS + t / WS, xs = wx * WS + t % WS;      // coordinates in the shifted, padded grid
   y = ys + g.shift; if (y >= g.Hp) y -= g.Hp;             // roll(-shift): shifted[ys] = x[(ys + shift) mod Hp]
   x = xs + g.shift; if (x >= g.Wp) x -= g.Wp;
@@ -42,8 +44,8 @@ __device__ __forceinline__ bool win_row_to_token(const SwinGeom& g, long r, int&
 __device__ __forceinline__ long token_to_win_row(const SwinGeom& g, int b, int y, int x) {
   int ys = y - g.shift; if (ys < 0) ys += g.Hp;
   int xs = x - g.shift; if (xs < 0) xs += g.Wp;
-  const long win = (static_cast<long>(b) * g.nwy + ys / WS) * g.nwx + xs / WS;
-  return win * WT + (ys % WS) * WS + xs % WS;
+  const int win = (b * g.nwy + ys / WS) * g.nwx + xs / WS;
+  return static_cast<long>(win) * WT + (ys % WS) * WS + xs % WS;
 }
 
 struct RowArgs {
@@ -64,7 +66,7 @@ template <int V4>
 __global__ void __launch_bounds__(256) swin_rows_kernel(const RowArgs a) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
-  const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int r = static_cast<int>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= a.rows) return;
   const SwinGeom& g = a.g;
   const int C = g.C;
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(256) swin_rows_kernel(const RowArgs a) {
   long tok;
   if (a.out_mode == 2) {
     if (!win_row_to_token(g, r, b, y, x)) {           // zero pad token (the reference pads after norm1, :236-240)
-      uint2* o = reinterpret_cast<uint2*>(a.out16 + r * C);
+      uint2* o = reinterpret_cast<uint2*>(a.out16 + static_cast<long>(r) * C);
 #pragma unroll
       for (int j = 0; j < V4; ++j) o[j * 32 + lane] = make_uint2(0u, 0u);
       return;
@@ -80,9 +82,10 @@ __global__ void __launch_bounds__(256) swin_rows_kernel(const RowArgs a) {
     tok = (static_cast<long>(b) * g.H + y) * g.W + x;
   } else {
     tok = r;
-    x = static_cast<int>(r % g.W);
-    y = static_cast<int>((r / g.W) % g.H);
-    b = static_cast<int>(r / (static_cast<long>(g.W) * g.H));
+    const int ry = r / g.W;
+    x = r - ry * g.W;
+    b = ry / g.H;
+    y = ry - b * g.H;
   }
   float v[V4 * 4];
   if (a.X != nullptr) {
@@ -159,11 +162,12 @@ swin_merge_kernel(const float* __restrict__ X, int B, int H, int W, int C, const
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
-  const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (r >= static_cast<long>(B) * H2 * W2) return;
-  const int x2 = static_cast<int>(r % W2);
-  const int y2 = static_cast<int>((r / W2) % H2);
-  const int b = static_cast<int>(r / (static_cast<long>(W2) * H2));
+  const int r = static_cast<int>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= B * H2 * W2) return;
+  const int ry = r / W2;
+  const int x2 = r - ry * W2;
+  const int b = ry / H2;
+  const int y2 = ry - b * H2;
   const int C4 = 4 * C;
   float v[V4 * 4];
 #pragma unroll
@@ -186,7 +190,7 @@ swin_merge_kernel(const float* __restrict__ X, int B, int H, int W, int C, const
     qq += d * d;
   }
   const float rstd = rsqrtf(warp_sum(qq) / static_cast<float>(C4) + 1e-5f);
-  uint2* op = reinterpret_cast<uint2*>(out + r * C4);
+  uint2* op = reinterpret_cast<uint2*>(out + static_cast<long>(r) * C4);
 #pragma unroll
   for (int j = 0; j < V4; ++j) {
     const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + j * 32 + lane);
@@ -207,9 +211,11 @@ __global__ void swin_patch_gather_kernel(const float* __restrict__ img, __half* 
   if (i >= total) return;
   const int q = static_cast<int>(i & 3);
   const long tok = i >> 2;
-  const int x4 = static_cast<int>(tok % W4);
-  const int y4 = static_cast<int>((tok / W4) % H4);
-  const int b = static_cast<int>(tok / (static_cast<long>(W4) * H4));
+  const int tk = static_cast<int>(tok);
+  const int ty4 = tk / W4;
+  const int x4 = tk - ty4 * W4;
+  const int b = ty4 / H4;
+  const int y4 = ty4 - b * H4;
   uint4 o[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
   if (q < 3) {
     const float mean = q == 0 ? m0 : (q == 1 ? m1 : m2);
@@ -395,6 +401,7 @@ int swin_rows_launch(float* X, int write_x, const void* add, int add_mode, const
   a.X = X; a.write_x = write_x; a.add = static_cast<const __half*>(add); a.add_mode = add_mode;
   a.gamma = gamma; a.beta = beta; a.out16 = static_cast<__half*>(out16); a.out32 = out32; a.out_mode = out_mode;
   a.rows = out_mode == 2 ? static_cast<long>(B) * a.g.nwy * a.g.nwx * WT : static_cast<long>(B) * H * W;
+  if (a.rows >= (1L << 31) - 8) return DVID_ERR_SHAPE;      // 32-bit row arithmetic in the kernel
   const unsigned grid = static_cast<unsigned>((a.rows + 7) / 8);
   switch (C / 128) {
     case 1: launch_pdl(swin_rows_kernel<1>, dim3(grid), dim3(256), 0, stream, a); break;
@@ -411,6 +418,7 @@ int swin_merge_launch(const float* X, int B, int H, int W, int C, const float* g
                       cudaStream_t stream) {
   if (B <= 0 || H <= 0 || W <= 0 || C % 128 != 0) return DVID_ERR_SHAPE;
   const long rows = static_cast<long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
+  if (rows >= (1L << 31) - 8) return DVID_ERR_SHAPE;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   __half* o = static_cast<__half*>(out);
   switch (4 * C / 128) {
@@ -426,6 +434,7 @@ int swin_patch_gather_launch(const float* img, void* out, int B, int H, int W, c
                              cudaStream_t stream) {
   if (B <= 0 || H % 4 != 0 || W % 4 != 0) return DVID_ERR_SHAPE;
   const long total = static_cast<long>(B) * (H / 4) * (W / 4) * 4;
+  if (total >= (1L << 31)) return DVID_ERR_SHAPE;
   launch_pdl(swin_patch_gather_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 
       img, static_cast<__half*>(out), B, H, W, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
   return check_launch();
