@@ -10,6 +10,8 @@ reference frames at the video start (backbone + 3 base stages on all 88 frames, 
   value : frames/s with the clip's images already resident in HBM when the timed region starts.
   e2e   : the same clip fed from pinned HOST memory (H2D copies of every ref frame inside the timed region) and the
           detections read back to the host (D2H) - the number to compare with the reference arm.
+  e2e_u8: the same call fed with the frames as decoded 8-bit images (uint8 ImageLists; SURVEY.md 8f-1 clip loader):
+          the reference's ToTensor is evaluated by the first GPU kernel, a quarter of the bytes cross PCIe.
   roofline : the dominant kernel family (tcgen05 conv/GEMM), algorithmic FLOPs / CUDA-event time measured live in a
           separate instrumented pass, against MEASURED_PEAKS.json (bf16 dense, sustained).
   cpu_baseline / --impl reference : the fp32 CPU oracle (oracle/model.py, a PyTorch restatement of the reference; the
@@ -172,11 +174,15 @@ class ClockSampler:
         return out
 
 
-def make_clip_inputs(args, dev, pinned):
-    """The per-frame `images` dicts of one clip.  pinned=True: host (pinned) tensors; else device-resident."""
+def make_clip_inputs(args, dev, pinned, u8=False):
+    """The per-frame `images` dicts of one clip.  pinned=True: host (pinned) tensors; else device-resident.
+    u8=True: the frames as decoded 8-bit images (clip-loader mode, SURVEY.md 8f-1: the reference's ToTensor runs inside
+    the first kernel instead of on the host)."""
     from diffusionvid_b200 import structures, synth
     L = args.frames
     frames = synth.make_clip(L, args.height, args.width, seed=1234)
+    if u8:
+        frames = (frames * 255.0).round().clamp(0, 255).to(torch.uint8)
     gidx = [(i * 7 + 3) % L for i in range(args.global_frames)]
     if pinned:
         store = frames.pin_memory()
@@ -195,7 +201,7 @@ def make_clip_inputs(args, dev, pinned):
                             ref_g=[structures.ImageList(store[i:i + 1], size) for i in ref_g],
                             frame_id=f, start_id=0, end_id=L - 1, seg_len=L, frame_category=0 if f == 0 else 1,
                             video_id=0))
-    img_bytes = frames[0].numel() * 4
+    img_bytes = frames[0].numel() * frames.element_size()
     n_ref = sum(len(s["ref_l"]) + len(s["ref_g"]) for s in samples)
     return samples, n_ref * img_bytes
 
@@ -279,6 +285,15 @@ def run_ours(args):
         ms_e2e, frames_e2e, _, d2h = timed(m, host_samples, args.steps, True, dist, dev)
         h2d_bytes = (m.io_bytes["h2d"] - io0["h2d"]) // max(1, args.steps)     # counted from the tensors copied
         d2h = m.io_bytes["d2h"] - io0["d2h"]
+        # clip-loader mode: the same clip as decoded 8-bit frames in pinned host memory (ToTensor fused on the GPU)
+        u8_samples, _ = make_clip_inputs(args, dev, pinned=True, u8=True)
+        for _ in range(2):
+            run_clip(m, u8_samples, True)
+        io1 = dict(m.io_bytes)
+        ms_u8, frames_u8, _, _ = timed(m, u8_samples, args.steps, True, dist, dev)
+        h2d_u8 = (m.io_bytes["h2d"] - io1["h2d"]) // max(1, args.steps)
+        d2h_u8 = (m.io_bytes["d2h"] - io1["d2h"]) // max(1, args.steps)
+        del u8_samples
         m.host_results = False
 
         roof = None
@@ -329,6 +344,7 @@ def run_ours(args):
     total_frames = frames * mult
     value = total_frames / (ms / 1000.0)
     e2e_value = frames_e2e * mult / (ms_e2e / 1000.0)
+    e2e_u8_value = frames_u8 * mult / (ms_u8 / 1000.0)
     if rank != 0:
         if dist:
             torch.distributed.destroy_process_group()
@@ -350,7 +366,12 @@ def run_ours(args):
                        "frames_per_step": args.frames, "l2": "inputs larger than L2 (clip %.0f MB fp32, feature maps "
                                                              "52 MB per key batch)" % (args.frames * 7.47)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": ms_e2e / args.steps,
+                    "input": "fp32 [0,1] ImageLists in pinned host memory (the reference's ToTensor output)"},
+            "e2e_u8": {"value": e2e_u8_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_u8,
+                       "d2h_bytes_per_step": d2h_u8, "ms_per_step": ms_u8 / args.steps,
+                       "input": "uint8 ImageLists in pinned host memory (decoded frames; ToTensor fused into "
+                                "dvid_preprocess_u8) - same public call"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
     if dist:

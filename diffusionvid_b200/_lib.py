@@ -26,6 +26,7 @@ SIGNATURES = {
     "dvid_stem_conv_f16": [P, P, P, P, I, I, I, I, I, P],
     "dvid_gemm_f16": [P, P, P, P, P, P, I, I, I, I, I, P, P],
     "dvid_preprocess": [P, P, I, I, I, I, I, I, P, P, P],
+    "dvid_preprocess_u8": [P, P, I, I, I, I, I, I, P, P, P],
     "dvid_maxpool3x3s2_nhwc_f16": [P, P, I, I, I, I, P],
     "dvid_attention_hd32": [P, P, P, P, I, I, I, I, L, L, L, L, L, L, L, L, P],
     "dvid_roi_align": [P, P, P, P, P, I, I, P, P, P, P],
@@ -46,6 +47,7 @@ SIGNATURES = {
     "dvid_swin_rows": [P, I, P, I, P, P, P, P, I, I, I, I, I, I, P],
     "dvid_swin_patch_merge": [P, I, I, I, I, P, P, P, P],
     "dvid_swin_patch_gather": [P, P, I, I, I, P, P, P],
+    "dvid_swin_patch_gather_u8": [P, P, I, I, I, P, P, P],
     "dvid_swin_window_attention": [P, P, P, I, I, I, I, I, I, P],
 }
 

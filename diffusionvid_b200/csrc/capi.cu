@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 7
+#define DVID_ABI_VERSION 8
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -45,7 +45,13 @@ int dvid_gemm_f16(const void* a, const void* w, const float* bias, const void* r
 int dvid_preprocess(const float* img, void* out, int n, int H, int W, int halo, int Hp, int Wp, const float* mean,
                     const float* std, void* stream) {
   if (!img || !out || !mean || !std) return DVID_ERR_ARG;
-  return dvid::preprocess_launch(img, out, n, H, W, halo, Hp, Wp, mean, std, S(stream));
+  return dvid::preprocess_launch(img, 0, out, n, H, W, halo, Hp, Wp, mean, std, S(stream));
+}
+
+int dvid_preprocess_u8(const unsigned char* img, void* out, int n, int H, int W, int halo, int Hp, int Wp,
+                       const float* mean, const float* std, void* stream) {
+  if (!img || !out || !mean || !std) return DVID_ERR_ARG;
+  return dvid::preprocess_launch(img, 1, out, n, H, W, halo, Hp, Wp, mean, std, S(stream));
 }
 
 int dvid_maxpool3x3s2_nhwc_f16(const void* in, void* out, int n, int H, int W, int C, void* stream) {
@@ -200,7 +206,13 @@ int dvid_swin_patch_merge(const float* x, int B, int H, int W, int C, const floa
 int dvid_swin_patch_gather(const float* img, void* out_f16, int B, int H, int W, const float* mean, const float* std,
                            void* stream) {
   if (!img || !out_f16 || !mean || !std) return DVID_ERR_ARG;
-  return dvid::swin_patch_gather_launch(img, out_f16, B, H, W, mean, std, S(stream));
+  return dvid::swin_patch_gather_launch(img, 0, out_f16, B, H, W, mean, std, S(stream));
+}
+
+int dvid_swin_patch_gather_u8(const unsigned char* img, void* out_f16, int B, int H, int W, const float* mean,
+                              const float* std, void* stream) {
+  if (!img || !out_f16 || !mean || !std) return DVID_ERR_ARG;
+  return dvid::swin_patch_gather_launch(img, 1, out_f16, B, H, W, mean, std, S(stream));
 }
 
 int dvid_swin_window_attention(const void* qkv, const float* bias, void* out_f16, int B, int H, int W, int C,

@@ -37,8 +37,8 @@ int roi_dynconv_launch(const void* const* feats, const int* hs, const int* ws, c
                        const float* g1, const float* b1, const float* g2, const float* b2, void* out,
                        cudaStream_t stream);
 
-int preprocess_launch(const float* img, void* out, int n, int H, int W, int halo, int Hp, int Wp, const float* mean,
-                      const float* std, cudaStream_t stream);
+int preprocess_launch(const void* img, int is_u8, void* out, int n, int H, int W, int halo, int Hp, int Wp,
+                      const float* mean, const float* std, cudaStream_t stream);
 int maxpool_launch(const void* in, void* out, int n, int H, int W, int C, cudaStream_t stream);
 int row_post_launch(const float* partials, int splits, long split_stride, const void* in_f16, const float* bias,
                     const float* ln1_g, const float* ln1_b, int relu1, const float* resid, const float* ln2_g,
@@ -80,8 +80,8 @@ int swin_rows_launch(float* X, int write_x, const void* add, int add_mode, const
                      cudaStream_t stream);
 int swin_merge_launch(const float* X, int B, int H, int W, int C, const float* gamma, const float* beta, void* out,
                       cudaStream_t stream);
-int swin_patch_gather_launch(const float* img, void* out, int B, int H, int W, const float* mean, const float* std,
-                             cudaStream_t stream);
+int swin_patch_gather_launch(const void* img, int is_u8, void* out, int B, int H, int W, const float* mean,
+                             const float* std, cudaStream_t stream);
 int swin_window_attention_launch(const void* qkv, const float* bias, void* out, int B, int H, int W, int C, int heads,
                                  int shift, cudaStream_t stream);
 

@@ -12,7 +12,15 @@ namespace {
 // ------------------------------------------------------------------------------------------------ preprocess
 // normalizer of mega_core/modeling/detector/diffusion_det.py:301-303,422: (x - mean/255) / (std/255), then NCHW fp32 ->
 // NHWC fp16 with 8 channels (3 real + 5 zero) and a zero halo of `halo` pixels (the stem convolution's padding).
-__global__ void preprocess_kernel(const float* __restrict__ img, __half* __restrict__ out, int n, int H, int W, int halo,
+//
+// T = uint8_t is the clip-loader variant: the frame arrives as the decoded 8-bit image and the
+// reference's ToTensor (mega_core/data/transforms/transforms.py:295-297, x = u8 / 255 in fp32) is evaluated here, so
+// the result is bit-identical to the fp32 entry while a quarter of the bytes cross PCIe and HBM.
+__device__ __forceinline__ float pixel_value(float v) { return v; }
+__device__ __forceinline__ float pixel_value(uint8_t v) { return __fdiv_rn(static_cast<float>(v), 255.f); }
+
+template <typename T>
+__global__ void preprocess_kernel(const T* __restrict__ img, __half* __restrict__ out, int n, int H, int W, int halo,
                                   int Hp, int Wp, float m0, float m1, float m2, float s0, float s1, float s2) {
   pdl_prologue();
   // grid (x blocks, padded row, image): no index arithmetic beyond adds (the first version decoded a flat 64-bit index
@@ -24,10 +32,10 @@ __global__ void preprocess_kernel(const float* __restrict__ img, __half* __restr
   uint4 v = make_uint4(0, 0, 0, 0);
   if (x >= 0 && x < W && y >= 0 && y < H) {
     const long plane = static_cast<long>(H) * W;
-    const float* p = img + static_cast<long>(im) * 3 * plane + static_cast<long>(y) * W + x;
-    const float r = __fdiv_rn(__fsub_rn(__ldg(p), m0), s0);
-    const float g = __fdiv_rn(__fsub_rn(__ldg(p + plane), m1), s1);
-    const float b = __fdiv_rn(__fsub_rn(__ldg(p + 2 * plane), m2), s2);
+    const T* p = img + static_cast<long>(im) * 3 * plane + static_cast<long>(y) * W + x;
+    const float r = __fdiv_rn(__fsub_rn(pixel_value(__ldg(p)), m0), s0);
+    const float g = __fdiv_rn(__fsub_rn(pixel_value(__ldg(p + plane)), m1), s1);
+    const float b = __fdiv_rn(__fsub_rn(pixel_value(__ldg(p + 2 * plane)), m2), s2);
     v.x = pack2h(r, g);
     v.y = pack2h(b, 0.f);
   }
@@ -392,12 +400,17 @@ inline int grid_for(long total, int block) {
 
 }  // namespace
 
-int preprocess_launch(const float* img, void* out, int n, int H, int W, int halo, int Hp, int Wp, const float* mean,
-                      const float* std, cudaStream_t stream) {
+int preprocess_launch(const void* img, int is_u8, void* out, int n, int H, int W, int halo, int Hp, int Wp,
+                      const float* mean, const float* std, cudaStream_t stream) {
   if (n <= 0 || H <= 0 || W <= 0 || Hp < H + 2 * halo || Wp < W + 2 * halo) return DVID_ERR_SHAPE;
   if (Hp > 65535 || n > 65535) return DVID_ERR_SHAPE;
-  launch_pdl(preprocess_kernel, dim3((Wp + 255) / 256, Hp, n), dim3(256), 0, stream, img, static_cast<__half*>(out), n, H, W, halo, Hp, Wp,
-                                                              mean[0], mean[1], mean[2], std[0], std[1], std[2]);
+  const dim3 grid((Wp + 255) / 256, Hp, n);
+  if (is_u8)
+    launch_pdl(preprocess_kernel<uint8_t>, grid, dim3(256), 0, stream, static_cast<const uint8_t*>(img),
+               static_cast<__half*>(out), n, H, W, halo, Hp, Wp, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
+  else
+    launch_pdl(preprocess_kernel<float>, grid, dim3(256), 0, stream, static_cast<const float*>(img),
+               static_cast<__half*>(out), n, H, W, halo, Hp, Wp, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
   return check_launch();
 }
 

@@ -202,7 +202,16 @@ swin_merge_kernel(const float* __restrict__ X, int B, int H, int W, int C, const
 
 // normalizer (diffusion_det.py:301-303) + 4x4/4 patch extraction (PatchEmbed, :422-461): img [B,3,H,W] fp32 ->
 // out [B*(H/4)*(W/4)][64] fp16, k = c*16 + py*4 + px (the flattening of proj.weight[embed][3][4][4]), k >= 48 zero.
-__global__ void swin_patch_gather_kernel(const float* __restrict__ img, __half* __restrict__ out, int B, int H, int W,
+// T = uint8_t: 8-bit frames with the reference's ToTensor (u8 / 255, transforms.py:295-297) evaluated here.
+__device__ __forceinline__ float4 load_px4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load_px4(const uint8_t* p) {
+  const uchar4 u = *reinterpret_cast<const uchar4*>(p);
+  return make_float4(__fdiv_rn(static_cast<float>(u.x), 255.f), __fdiv_rn(static_cast<float>(u.y), 255.f),
+                     __fdiv_rn(static_cast<float>(u.z), 255.f), __fdiv_rn(static_cast<float>(u.w), 255.f));
+}
+
+template <typename T>
+__global__ void swin_patch_gather_kernel(const T* __restrict__ img, __half* __restrict__ out, int B, int H, int W,
                                          float m0, float m1, float m2, float s0, float s1, float s2) {
   pdl_prologue();
   const int H4 = H / 4, W4 = W / 4;
@@ -220,11 +229,11 @@ __global__ void swin_patch_gather_kernel(const float* __restrict__ img, __half* 
   if (q < 3) {
     const float mean = q == 0 ? m0 : (q == 1 ? m1 : m2);
     const float sd = q == 0 ? s0 : (q == 1 ? s1 : s2);
-    const float* p = img + ((static_cast<long>(b) * 3 + q) * H + y4 * 4) * W + x4 * 4;
+    const T* p = img + ((static_cast<long>(b) * 3 + q) * H + y4 * 4) * W + x4 * 4;
     uint32_t w[8];
 #pragma unroll
     for (int py = 0; py < 4; ++py) {
-      const float4 f = *reinterpret_cast<const float4*>(p + static_cast<long>(py) * W);
+      const float4 f = load_px4(p + static_cast<long>(py) * W);
       w[2 * py] = pack2h(__fdiv_rn(__fsub_rn(f.x, mean), sd), __fdiv_rn(__fsub_rn(f.y, mean), sd));
       w[2 * py + 1] = pack2h(__fdiv_rn(__fsub_rn(f.z, mean), sd), __fdiv_rn(__fsub_rn(f.w, mean), sd));
     }
@@ -430,13 +439,18 @@ int swin_merge_launch(const float* X, int B, int H, int W, int C, const float* g
   return check_launch();
 }
 
-int swin_patch_gather_launch(const float* img, void* out, int B, int H, int W, const float* mean, const float* std,
-                             cudaStream_t stream) {
+int swin_patch_gather_launch(const void* img, int is_u8, void* out, int B, int H, int W, const float* mean,
+                             const float* std, cudaStream_t stream) {
   if (B <= 0 || H % 4 != 0 || W % 4 != 0) return DVID_ERR_SHAPE;
   const long total = static_cast<long>(B) * (H / 4) * (W / 4) * 4;
   if (total >= (1L << 31)) return DVID_ERR_SHAPE;
-  launch_pdl(swin_patch_gather_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, 
-      img, static_cast<__half*>(out), B, H, W, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
+  const dim3 grid(static_cast<unsigned>((total + 255) / 256));
+  if (is_u8)
+    launch_pdl(swin_patch_gather_kernel<uint8_t>, grid, dim3(256), 0, stream, static_cast<const uint8_t*>(img),
+               static_cast<__half*>(out), B, H, W, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
+  else
+    launch_pdl(swin_patch_gather_kernel<float>, grid, dim3(256), 0, stream, static_cast<const float*>(img),
+               static_cast<__half*>(out), B, H, W, mean[0], mean[1], mean[2], std[0], std[1], std[2]);
   return check_launch();
 }
 

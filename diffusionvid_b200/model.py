@@ -45,6 +45,12 @@ def _register(root, name, tensor, buffer):
         m.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
 
 
+def _frame_dtype(t):
+    """Frames stay uint8 when they arrive as decoded 8-bit images (clip-loader mode, SURVEY.md 8f-1: ToTensor is fused
+    into the first kernel and a quarter of the bytes cross PCIe); anything else is the reference's fp32 [0,1] tensor."""
+    return torch.uint8 if t.dtype == torch.uint8 else F32
+
+
 def _cosine_alphas_cumprod(timesteps=1000, s=0.008):
     """diffusion_det.py:50-61,226-228."""
     x = torch.linspace(0, timesteps, timesteps + 1, dtype=torch.float64)
@@ -876,7 +882,7 @@ class DiffusionDet(nn.Module):
             self._copy_stream = torch.cuda.Stream()
         self.io_bytes["h2d"] += t.numel() * t.element_size()
         with torch.cuda.stream(self._copy_stream):
-            d = t.to(dev, F32, non_blocking=True)
+            d = t.to(dev, _frame_dtype(t), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return (d, ev)
@@ -890,7 +896,7 @@ class DiffusionDet(nn.Module):
             return d
         if not item.tensors.is_cuda:
             self.io_bytes["h2d"] += item.tensors.numel() * item.tensors.element_size()
-        return item.tensors.to(dev, F32, non_blocking=True)
+        return item.tensors.to(dev, _frame_dtype(item.tensors), non_blocking=True)
 
     def _results_on_host(self, r, batch, cap, w, h):
         """`host_results` mode: ONE device->host copy per key batch (count | boxes | scores | labels packed in fp32; counts

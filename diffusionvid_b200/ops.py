@@ -128,14 +128,16 @@ def gemm_partials(a, w, splits=1, out=None):
 
 # ------------------------------------------------------------------------------------------------ image side
 def preprocess(img, mean, std, halo=3):
-    """img [n,3,H,W] fp32 in [0,1] -> [n, H+2*halo, W+2*halo, 8] fp16 normalised, zero halo."""
-    _chk(img, F32, "img")
+    """img [n,3,H,W] fp32 in [0,1], or uint8 as decoded (the reference's ToTensor, transforms.py:295-297, is then
+    evaluated inside the kernel) -> [n, H+2*halo, W+2*halo, 8] fp16 normalised, zero halo."""
+    u8 = img.dtype == torch.uint8
+    _chk(img, torch.uint8 if u8 else F32, "img")
     n, _, h, w = img.shape
     out = torch.empty((n, h + 2 * halo, w + 2 * halo, 8), device=img.device, dtype=H)
     m = (ctypes.c_float * 3)(*mean)
     s = (ctypes.c_float * 3)(*std)
-    check(_lib.lib().dvid_preprocess(ptr(img), ptr(out), n, h, w, halo, h + 2 * halo, w + 2 * halo, m, s,
-                                     cur_stream()), "dvid_preprocess")
+    fn = _lib.lib().dvid_preprocess_u8 if u8 else _lib.lib().dvid_preprocess
+    check(fn(ptr(img), ptr(out), n, h, w, halo, h + 2 * halo, w + 2 * halo, m, s, cur_stream()), "dvid_preprocess")
     _cnt()
     return out
 
@@ -389,12 +391,14 @@ def swin_patch_merge(x, ln):
 
 
 def swin_patch_gather(img, mean, std):
-    _chk(img, F32, "img")
+    u8 = img.dtype == torch.uint8
+    _chk(img, torch.uint8 if u8 else F32, "img")
     B, _, Hh, W = img.shape
     out = torch.empty((B * (Hh // 4) * (W // 4), 64), device=img.device, dtype=H)
     m = (ctypes.c_float * 3)(*mean)
     s = (ctypes.c_float * 3)(*std)
-    check(_lib.lib().dvid_swin_patch_gather(ptr(img), ptr(out), B, Hh, W, m, s, cur_stream()), "dvid_swin_patch_gather")
+    fn = _lib.lib().dvid_swin_patch_gather_u8 if u8 else _lib.lib().dvid_swin_patch_gather
+    check(fn(ptr(img), ptr(out), B, Hh, W, m, s, cur_stream()), "dvid_swin_patch_gather")
     _cnt()
     return out
 

@@ -76,6 +76,11 @@ DVID_API int dvid_gemm_f16(const void* a, const void* w, const float* bias, cons
  * img [n][3][H][W] in [0,1]; out [n][Hp][Wp][8]; mean/std: 3 host floats (already divided by 255). */
 DVID_API int dvid_preprocess(const float* img, void* out, int n, int H, int W, int halo, int Hp, int Wp, const float* mean,
                     const float* std, void* stream);
+/* Clip-loader variant: img [n][3][H][W] uint8 as decoded; fuses the reference's ToTensor
+ * (mega_core/data/transforms/transforms.py:295-297 = torchvision to_tensor: u8 -> fp32 / 255, applied by
+ * transforms/build.py:75-83) in front of the normalizer.  Output bit-identical to dvid_preprocess(to_tensor(img)). */
+DVID_API int dvid_preprocess_u8(const unsigned char* img, void* out, int n, int H, int W, int halo, int Hp, int Wp,
+                       const float* mean, const float* std, void* stream);
 /* max_pool2d(kernel 3, stride 2, pad 1) of the stem, NHWC fp16, C % 8 == 0. */
 DVID_API int dvid_maxpool3x3s2_nhwc_f16(const void* in, void* out, int n, int H, int W, int C, void* stream);
 
@@ -201,6 +206,9 @@ DVID_API int dvid_swin_patch_merge(const float* x, int B, int H, int W, int C, c
  * out_f16 [B*(H/4)*(W/4)][64], k = c*16 + py*4 + px, k >= 48 zero.  mean/std: 3 host floats (already / 255). */
 DVID_API int dvid_swin_patch_gather(const float* img, void* out_f16, int B, int H, int W, const float* mean,
                            const float* std, void* stream);
+/* uint8 frames (ToTensor fused, see dvid_preprocess_u8); W % 4 == 0 keeps the 4-pixel loads aligned. */
+DVID_API int dvid_swin_patch_gather_u8(const unsigned char* img, void* out_f16, int B, int H, int W, const float* mean,
+                              const float* std, void* stream);
 /* WindowAttention core (:145-176): softmax(q*scale k^T + bias + shift mask) v per (window, head), head dim 32.
  * qkv [windows*49][3C] fp16 in shifted-window order, bias [heads][49][49] fp32 (table gathered by
  * relative_position_index), out_f16 [windows*49][C].  The SW-MSA mask of BasicLayer.forward (:387-406) is derived from

@@ -104,6 +104,20 @@ class Ctx:
     def __init__(self, sd, quant):
         self.sd = sd
         self.q = quant
+        self._folded = {}
+
+    def folded(self, name):
+        """FrozenBatchNorm2d(eps=1e-5) folded into the conv: w' = w*scale, b' = beta - mean*scale (the state dict is
+        constant for the life of the oracle, so the folded pair is computed once per conv)."""
+        if name not in self._folded:
+            sd = self.sd
+            scale = sd[name + ".norm.weight"] * torch.rsqrt(sd[name + ".norm.running_var"] + 1e-5)
+            shift = sd[name + ".norm.bias"] - sd[name + ".norm.running_mean"] * scale
+            wf = sd[name + ".weight"] * scale[:, None, None, None]
+            if self.q.enabled:
+                wf = wf.half().float()
+            self._folded[name] = (wf, shift)
+        return self._folded[name]
 
     def lin(self, x, name, bias=True, out16=False, round_in=True):
         w = self.q.w(self.sd[name + ".weight"])
@@ -123,13 +137,7 @@ class Ctx:
 def _conv_bn(c, x, name, stride, pad, relu, resid=None):
     """conv (no bias) + FrozenBatchNorm2d(eps=1e-5) folded: w' = w*scale, b' = beta - mean*scale; optional residual;
     ReLU; output rounded to fp16 in emulation mode (the kernels store NHWC fp16)."""
-    sd = c.sd
-    w = sd[name + ".weight"]
-    scale = sd[name + ".norm.weight"] * torch.rsqrt(sd[name + ".norm.running_var"] + 1e-5)
-    shift = sd[name + ".norm.bias"] - sd[name + ".norm.running_mean"] * scale
-    wf = w * scale[:, None, None, None]
-    if c.q.enabled:
-        wf = wf.half().float()
+    wf, shift = c.folded(name)
     y = F.conv2d(x, wf, shift, stride=stride, padding=pad)
     if resid is not None:
         y = y + resid
@@ -231,7 +239,7 @@ def attention(c, xq, xkv, name, nheads):
 def time_embedding(c, t, dim=256):
     """box_head.py:218-223,729-741: sinusoid -> Linear -> GELU -> Linear.  t (B,) -> (B, 4*dim)."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    freq = torch.exp(torch.arange(half, dtype=torch.float32, device=t.device) * -(math.log(10000) / (half - 1)))
     e = t.float()[:, None] * freq[None, :]
     e = torch.cat((e.sin(), e.cos()), dim=-1)
     e = c.lin(e, "head.time_mlp.1", round_in=False)
@@ -328,8 +336,8 @@ def update_erase_memory(feats_new, feats_mem, target):
     if merged.shape[0] <= target:
         return merged
     dist = ops.cdist_l2(merged.contiguous())
-    idx = ops.fps(dist.numpy(), target)
-    return merged[torch.from_numpy(idx).long()]
+    idx = ops.fps(dist.cpu().numpy(), target)
+    return merged[torch.from_numpy(idx).long().to(merged.device)]
 
 
 def topk_scores(logits_frame, boxes_frame, n):
@@ -393,8 +401,8 @@ class OracleDiffusionVID:
         return torch.clamp(xs, min=-s, max=s)
 
     def backbone(self, imgs):
-        mean = torch.tensor(self.cfg["pixel_mean"]).view(1, 3, 1, 1) / 255.
-        std = torch.tensor(self.cfg["pixel_std"]).view(1, 3, 1, 1) / 255.
+        mean = (torch.tensor(self.cfg["pixel_mean"]).view(1, 3, 1, 1) / 255.).to(imgs.device)
+        std = (torch.tensor(self.cfg["pixel_std"]).view(1, 3, 1, 1) / 255.).to(imgs.device)
         if "backbone.bottom_up.patch_embed.proj.weight" in self.c.sd:      # vid_Swin_B_DiffusionVID.yaml
             from . import swin
             return swin.swin_fpn(self.c, (imgs - mean) / std)
@@ -418,7 +426,8 @@ class OracleDiffusionVID:
         ref_l = self.local_img_queue + list(s["ref_l"])
         self.local_img_queue = []
         h, w = s["image_size"]
-        whwh1 = torch.tensor([w, h, w, h], dtype=torch.float32)
+        dev = s["cur"].device        # CPU everywhere except the library-kernel timing bar (tests/test_gpu_library_bar.py)
+        whwh1 = torch.tensor([w, h, w, h], dtype=torch.float32, device=dev)
 
         if ref_l or s["ref_g"]:
             imgs = torch.cat(ref_l + list(s["ref_g"]))
@@ -428,8 +437,8 @@ class OracleDiffusionVID:
                 f = self.backbone(split)
                 B = split.shape[0]
                 whwh = whwh1[None].expand(B, -1)
-                box_init = self.noise.get("init", self.video, fid, bi, B)
-                t = torch.full((B,), 999, dtype=torch.long)
+                box_init = self.noise.get("init", self.video, fid, bi, B).to(dev)
+                t = torch.full((B,), 999, dtype=torch.long, device=dev)
                 temb = time_embedding(c, t)
                 lg, bx, obj = head_base_stages(c, f, self._x_to_boxes(box_init, whwh), temb, cfg)
                 k1, k2 = select_topk_feats(lg, obj, B, N, [min(k, N) for k in cfg["topk"]])
@@ -464,11 +473,11 @@ class OracleDiffusionVID:
         times = torch.linspace(-1, 999, steps=T + 1)
         times = list(reversed(times.int().tolist()))
         pairs = list(zip(times[:-1], times[1:]))
-        img = self.noise.get("img", self.video, fid, 0, batch)
+        img = self.noise.get("img", self.video, fid, 0, batch).to(dev)
         ens = []
         logits = coord = None
         for si, (time, time_next) in enumerate(pairs):
-            t = torch.full((batch,), time, dtype=torch.long)
+            t = torch.full((batch,), time, dtype=torch.long, device=dev)
             temb = time_embedding(c, t)
             if T > 1:
                 lg, bx, obj = head_base_stages(c, feats_cur, self._x_to_boxes(img, whwh), temb, cfg)
@@ -493,8 +502,8 @@ class OracleDiffusionVID:
             sigma = (1.0 * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()).to(torch.float32)
             cc = (1 - an - ((1 - a / an) * (1 - an) / (1 - a))).sqrt().to(torch.float32)
             san = self.alphas_cumprod[time_next].sqrt()
-            eps = self.noise.get("eps", self.video, fid, si, batch)
-            fillz = self.noise.get("fill", self.video, fid, si, batch)
+            eps = self.noise.get("eps", self.video, fid, si, batch).to(dev)
+            fillz = self.noise.get("fill", self.video, fid, si, batch).to(dev)
             new = []
             for i in range(batch):
                 kx = x_start[i, keep[i]]

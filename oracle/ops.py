@@ -32,8 +32,9 @@ def roi_align(feat, rois, out_size, scale, sampling_ratio):
     y2 = rois[:, 4] * scale - 0.5
     bin_w = (x2 - x1) / P
     bin_h = (y2 - y1) / P
-    pbin = (torch.arange(P * S) // S).to(feat.dtype)[None, :]              # ph for each of the P*S sample rows
-    frac = ((torch.arange(P * S) % S).to(feat.dtype) + 0.5)[None, :]       # iy + .5
+    ar = torch.arange(P * S, device=feat.device)
+    pbin = (ar // S).to(feat.dtype)[None, :]                               # ph for each of the P*S sample rows
+    frac = ((ar % S).to(feat.dtype) + 0.5)[None, :]                        # iy + .5
     # torchvision: y = roi_start_h + ph * bin_size_h + (iy + .5f) * bin_size_h / roi_bin_grid_h  (same op order)
     ys = y1[:, None] + pbin * bin_h[:, None] + frac * bin_h[:, None] / S   # (K, P*S)
     xs = x1[:, None] + pbin * bin_w[:, None] + frac * bin_w[:, None] / S
@@ -92,7 +93,7 @@ def roi_pooler(feats, boxes, scales=(1 / 8., 1 / 16., 1 / 32.), out_size=7, samp
     """
     B, N = boxes.shape[:2]
     flat = boxes.reshape(-1, 4)
-    bcol = torch.arange(B, dtype=flat.dtype).repeat_interleave(N)[:, None]
+    bcol = torch.arange(B, dtype=flat.dtype, device=flat.device).repeat_interleave(N)[:, None]
     rois = torch.cat([bcol, flat], dim=1)
     lvl = assign_levels(flat, 3, 3 + len(feats) - 1)
     out = feats[0].new_zeros((B * N, feats[0].shape[1], out_size, out_size))

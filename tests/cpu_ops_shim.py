@@ -65,6 +65,8 @@ def gemm_partials(a, w, splits=1, out=None):
 def preprocess(img, mean, std, halo=3):
     m = torch.tensor(mean, dtype=F32).view(1, 3, 1, 1)
     s = torch.tensor(std, dtype=F32).view(1, 3, 1, 1)
+    if img.dtype == torch.uint8:          # clip-loader mode: ToTensor (u8 / 255) fused into the kernel
+        img = img.to(F32).div(255)
     x = ((img - m) / s).half()
     n, _, h, w = img.shape
     out = torch.zeros((n, h + 2 * halo, w + 2 * halo, 8), dtype=H)

@@ -170,3 +170,30 @@ def test_host_fed_pipeline_equals_device_resident_path(cuda, T):
     assert fr[len(fr) // 2] >= 0.95, fracs
     if T == 1:
         assert sum(fracs) / len(fracs) >= 0.95, fracs
+
+
+def test_uint8_frames_equal_fp32_frames(cuda):
+    """Clip-loader mode: the same clip delivered as decoded 8-bit frames (uint8 ImageLists in pinned
+    host memory, ToTensor fused into dvid_preprocess_u8) must give exactly the detections of the reference protocol
+    (ToTensor on the host, fp32 ImageLists) - the first kernel's output is bit-identical and everything after it runs
+    on the same batch compositions - while a quarter of the bytes cross PCIe."""
+    h, w, L = 192, 256, 19
+    u8 = (synth.make_clip(L, h, w, seed=6) * 255.0).round().clamp(0, 255).to(torch.uint8)
+    outs, sent = [], []
+    for frames in (u8.to(torch.float32).div(255).pin_memory(), u8.pin_memory()):
+        hp, sd, m, noise, ocfg = _models(4)
+        m.host_results = True
+        res = []
+        for s in synth.clip_samples(frames, [17, 3, 9, 12], h, w):
+            got = m(dict(cur=structures.ImageList(s["cur"], [(h, w)]),
+                         ref_l=[structures.ImageList(t, [(h, w)]) for t in s["ref_l"]],
+                         ref_g=[structures.ImageList(t, [(h, w)]) for t in s["ref_g"]],
+                         frame_id=s["frame_id"], start_id=0, end_id=s["end_id"], seg_len=L,
+                         frame_category=s["frame_category"], video_id=0))
+            res += [(b.bbox.cpu(), b.get_field("scores").cpu(), b.get_field("labels").cpu()) for b in got]
+        outs.append(res)
+        sent.append(m.io_bytes["h2d"])
+    assert len(outs[0]) == len(outs[1]) == L
+    assert sent[0] == 4 * sent[1] and sent[1] == (L + 4) * 3 * h * w
+    for (b0, s0, l0), (b1, s1, l1) in zip(*outs):
+        assert torch.equal(b0, b1) and torch.equal(s0, s1) and torch.equal(l0, l1)

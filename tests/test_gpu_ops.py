@@ -371,6 +371,29 @@ def test_preprocess_maxpool_stem(cuda):
     assert torch.equal(p.float().cpu(), pref)
 
 
+def test_preprocess_u8_equals_totensor_then_fp32_entry(cuda):
+    """Clip-loader entry: uint8 frames with the reference's ToTensor (transforms.py:295-297 =
+    torchvision to_tensor: u8.float().div(255)) fused must be BIT-identical to ToTensor on the host followed by the
+    fp32 entry - R-101 stem layout and Swin patch gather; every 8-bit value and ragged widths are covered."""
+    g = gen(47)
+    mean = [123.675 / 255, 116.28 / 255, 103.53 / 255]; std = [58.395 / 255, 57.12 / 255, 57.375 / 255]
+    for n, Hh, W in ((2, 37, 301), (1, 64, 256)):
+        u8 = torch.randint(0, 256, (n, 3, Hh, W), generator=g, dtype=torch.uint8)
+        u8[0, :, 0, :256] = torch.arange(256, dtype=torch.uint8)           # all 256 codes in every channel
+        f32 = u8.to(torch.float32).div(255)
+        a = ops.preprocess(u8.to(cuda), mean, std, halo=3)
+        b = ops.preprocess(f32.to(cuda), mean, std, halo=3)
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+        mt = torch.tensor(mean).view(1, 3, 1, 1); st = torch.tensor(std).view(1, 3, 1, 1)
+        assert torch.equal(a.cpu()[:, 3:-3, 3:-3, :3], ((f32 - mt) / st).half().permute(0, 2, 3, 1))
+    u8 = torch.randint(0, 256, (2, 3, 32, 64), generator=g, dtype=torch.uint8)
+    a = ops.swin_patch_gather(u8.to(cuda), mean, std)
+    b = ops.swin_patch_gather(u8.to(torch.float32).div(255).to(cuda), mean, std)
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+    with pytest.raises(Exception):
+        ops.preprocess(u8.to(cuda).to(torch.int32), mean, std)           # only fp32 / uint8 frames are accepted
+
+
 @pytest.mark.parametrize("M", [100, 2400])
 def test_fused_head_tail_matches_layerwise_math(cuda, M):
     """dvid_head_tail (cls tower -> logits, 3 x reg tower -> deltas -> apply_deltas, box_head.py:538-590) vs the same

@@ -169,6 +169,44 @@ def test_clip_state_machine_matches_oracle_with_shimmed_ops(shim, T, L):
     assert same_count >= 0.5 * L
 
 
+def test_uint8_frames_follow_the_fp32_protocol(shim):
+    """Clip-loader mode: uint8 ImageLists stay uint8 up to the first operator (where ToTensor,
+    transforms.py:295-297, is fused) and give the detections of the fp32 protocol on the same 8-bit clip."""
+    h, w, L = 96, 128, 9
+    hp = dict(SMALL, sample_step=1)
+    sd = synth.make_state_dict(seed=11, blocks=hp["blocks"])
+    u8 = (synth.make_clip(L, h, w, seed=5) * 255.0).round().clamp(0, 255).to(torch.uint8)
+    seen = []
+    real = cpu_ops_shim.preprocess
+
+    def spy(img, *a, **kw):
+        seen.append(img.dtype)
+        return real(img, *a, **kw)
+    outs = []
+    for frames in (u8.to(torch.float32).div(255), u8):
+        m = pm.DiffusionDet(hp)
+        m.load_state_dict(sd, strict=False)
+        m.noise = om.NoiseSource(3, hp["num_proposals"])
+        seen.clear()
+        cpu_ops_shim.preprocess = spy
+        try:
+            res = []
+            for s in synth.clip_samples(frames, [L - 1, 2, 5, 3], h, w):
+                got = m(dict(cur=structures.ImageList(s["cur"], [(h, w)]),
+                             ref_l=[structures.ImageList(t, [(h, w)]) for t in s["ref_l"]],
+                             ref_g=[structures.ImageList(t, [(h, w)]) for t in s["ref_g"]],
+                             frame_id=s["frame_id"], start_id=0, end_id=s["end_id"], seg_len=L,
+                             frame_category=s["frame_category"], video_id=0))
+                res += [(b.bbox, b.get_field("scores"), b.get_field("labels")) for b in got]
+        finally:
+            cpu_ops_shim.preprocess = real
+        assert seen and all(d == frames.dtype for d in seen)
+        outs.append(res)
+    assert len(outs[0]) == len(outs[1]) == L
+    for (b0, s0, l0), (b1, s1, l1) in zip(*outs):
+        assert torch.equal(b0, b1) and torch.equal(s0, s1) and torch.equal(l0, l1)
+
+
 def test_package_exports():
     assert diffusionvid_b200.__version__
     assert hasattr(diffusionvid_b200, "build_detection_model")
