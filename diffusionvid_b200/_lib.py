@@ -21,6 +21,7 @@ F = ctypes.c_float
 # name -> argtypes; every entry point returns int.  Kept in the order of include/dvid_b200.h.
 SIGNATURES = {
     "dvid_abi_version": [],
+    "dvid_conv_streamk": [I],
     "dvid_num_sms": [],
     "dvid_conv2d_nhwc_f16": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dvid_stem_conv_f16": [P, P, P, P, I, I, I, I, I, P],

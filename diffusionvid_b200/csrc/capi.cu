@@ -42,6 +42,8 @@ int dvid_gemm_f16(const void* a, const void* w, const float* bias, const void* r
                                 n, 1, 1, 1, 0, 0, relu, splits, 0, S(stream));
 }
 
+int dvid_conv_streamk(int enable) { return dvid::conv_streamk_enable(enable); }
+
 int dvid_preprocess(const float* img, void* out, int n, int H, int W, int halo, int Hp, int Wp, const float* mean,
                     const float* std, void* stream) {
   if (!img || !out || !mean || !std) return DVID_ERR_ARG;

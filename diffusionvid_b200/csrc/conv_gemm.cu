@@ -66,7 +66,18 @@ struct ConvGemmParams {
   // tile and a 32-bit integer division is a ~35-instruction dependent chain - five of them cost the epilogue ~0.4 us
   // per tile (device trace), as much as converting a 64-column chunk
   FastDiv div_m_tiles, div_n_tiles, div_tiles_x, div_tiles_y;
-  unsigned long long* trace;   // DVID_TRACE: per-role event log of CTA 0 (debug only), else nullptr
+  unsigned long long* trace;   // DVID_TRACE: per-role event log of CTA `trace_cta` (debug only), else nullptr
+  int trace_cta;               // DVID_TRACE_CTA (default 0)
+  // stream-K (SK variants only): fp32 partial accumulator tiles [grid][BN/4][128][4] and one flag per CTA
+  // weights are independent of the previous kernel: every CTA asks L2 for its slice of them BEFORE griddepcontrol.wait,
+  // while the previous kernel is still draining (its output, our A operand, is the only thing we have to wait for)
+  const uint8_t* w_base;
+  unsigned w_slice_bytes;      // 0: no prefetch; else multiple of 128
+  unsigned long long w_bytes;
+  int b_pre;                   // BSTAT: first resident weight tile requested before the dependency wait (DVID_BPRE)
+  float* sk_ws;
+  unsigned* sk_flags;
+  FastDiv div_total_kb;
 };
 
 // BSTAT ("B-stationary", K <= 256): the whole [BN x K] weight tile stays resident in smem while the CTA walks a
@@ -84,6 +95,16 @@ constexpr int BAR_FULL0 = 2, BAR_FREE0 = 4, BAR_BIAS0 = 6;
 // 16-byte global loads, which cost 3-4 us per 64-column chunk (device trace: profiles/r01_trace_res4_conv3.txt).
 constexpr int IDENT_BYTES = 16 * 128;   // 16 rows (n) x 64 k fp16, 128-byte swizzle; I[n][k] = (n == k), k < 16
 
+// SK ("stream-K"): the (tile, k-block) space is cut into gridDim.x equal contiguous ranges instead of whole tiles, so a
+// layer of 152 tiles costs 152/148 of a wave instead of two (res4: 8 frames x 38x64 pixels = 152 M tiles, 46 of the
+// 104 backbone convs).  With tiles >= CTAs every range is at least one tile long, so a tile is shared by at most two
+// CTAs: the range of CTA b ends with the HEAD k-blocks of a tile whose TAIL k-blocks open the range of CTA b+1.  A CTA
+// runs its head segment FIRST and parks the fp32 accumulator tile in its workspace slot (coalesced: 4 columns x 128
+// rows per 2 KB) and raises a flag; the tail owner adds the parked tile in its epilogue and finishes the tile (bias /
+// residual / activation / TMA store) as usual.  The parked tile is the producer's first item and depends on nothing,
+// CTAs are dispatched in index order and are co-resident (1 per SM, grid <= SMs): no deadlock, and both sides of the
+// hand-off overlap a main loop (the first version parked tails and finished heads as each CTA's LAST item: the
+// exposed wait + 128 KB read cost as much as the saved second wave).
 template <int BN, bool BSTAT = false, bool RES = false>
 struct ConvGemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
@@ -116,7 +137,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 // debug event log (DVID_TRACE=1): role r appends (code, clock) pairs to its own 1024-entry lane of p.trace, CTA 0 only
 __device__ __forceinline__ void trace_ev(const ConvGemmParams& p, int role, int& n, unsigned code) {
-  if (p.trace != nullptr && blockIdx.x == 0 && n < 1023) {
+  if (p.trace != nullptr && blockIdx.x == p.trace_cta && n < 1023) {
     const unsigned long long t = static_cast<unsigned long long>(clock64());   // SM-local cycles (cheap)
     p.trace[role * 2048 + 2 * n] = code;
     p.trace[role * 2048 + 2 * n + 1] = t;
@@ -124,7 +145,17 @@ __device__ __forceinline__ void trace_ev(const ConvGemmParams& p, int role, int&
   }
 }
 
-template <int BN, bool BSTAT, bool RES>
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr int BAR_SK = 8;   // named barrier of the eight epilogue warps (stream-K hand-off)
+
+template <int BN, bool BSTAT, bool RES, bool SK>
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -172,6 +203,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 3 && p.w_slice_bytes != 0 && elect_one()) {
+    const unsigned long long off = static_cast<unsigned long long>(blockIdx.x) * p.w_slice_bytes;
+    if (off < p.w_bytes) {
+      const unsigned long long left = p.w_bytes - off;
+      const unsigned n = left < p.w_slice_bytes ? static_cast<unsigned>(left) & ~15u : p.w_slice_bytes;
+      if (n != 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.w_base + off), "r"(n) : "memory");
+    }
+  }
   if (RES && warp >= 4) {
     // identity B tile: row n (16 rows of 128 B), element k at 16-byte chunk (k / 8) ^ (n & 7)
     const int t = threadIdx.x - 128;
@@ -191,7 +231,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int tw = 1 << p.tw_log2;
@@ -221,16 +260,81 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     kb_begin = split * p.kb_per_split;
     kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
   };
+  // work walk: every role iterates the same (tile, k-block range) items.  Normal: whole tiles (or split-K slices).
+  // SK: this CTA's contiguous range [sk_u0, sk_u1) of the flattened (tile, k-block) space, cut at tile boundaries.
+  static_assert(!SK || (!BSTAT && !RES), "stream-K serves the plain variants only");
+  int sk_u0 = 0, sk_u1 = 0, sk_uh = 0;
+  if (SK) {
+    const long long units = static_cast<long long>(total_tiles) * p.total_kb;
+    sk_u0 = static_cast<int>(units * blockIdx.x / gridDim.x);
+    sk_u1 = static_cast<int>(units * (blockIdx.x + 1) / gridDim.x);
+    sk_uh = p.div_total_kb.div(sk_u1) * p.total_kb;     // start of the trailing HEAD segment (== sk_u1: none)
+  }
+  // SK item order: the trailing head segment FIRST (its accumulator is parked for the next CTA while this CTA's other
+  // items run), then the range in order - a leading tail segment (finished with the tile parked by CTA b-1, whose
+  // first item that was) and whole tiles.  Every hand-off therefore overlaps a main loop; nothing waits at the end.
+  struct Walk { int tile, kb0, kb1, u; bool head; };
+  auto walk_set = [&](Walk& w) {
+    if (SK) {
+      const int limit = w.head ? sk_u1 : sk_uh;
+      if (w.u < limit) {
+        w.tile = p.div_total_kb.div(w.u);
+        w.kb0 = w.u - w.tile * p.total_kb;
+        w.kb1 = min(p.total_kb, w.kb0 + (limit - w.u));
+      }
+    }
+  };
+  auto walk_begin = [&]() {
+    Walk w;
+    w.tile = tile_begin; w.kb0 = 0; w.kb1 = 0;
+    w.head = SK && sk_uh < sk_u1;
+    w.u = w.head ? sk_uh : sk_u0;
+    walk_set(w);
+    return w;
+  };
+  auto walk_valid = [&](const Walk& w) { return SK ? (w.head || w.u < sk_uh) : (w.tile < tile_end); };
+  auto walk_next = [&](Walk& w) {
+    if (SK) {
+      if (w.head) { w.head = false; w.u = sk_u0; }
+      else w.u += w.kb1 - w.kb0;
+      walk_set(w);
+    } else {
+      w.tile += tile_step;
+    }
+  };
+  auto walk_k = [&](const Walk& w, int split, int& kb_begin, int& kb_end) {
+    if (SK) { kb_begin = w.kb0; kb_end = w.kb1; }
+    else k_range(split, kb_begin, kb_end);
+  };
+
+  // BSTAT: the first resident weight tile (up to 128 KB per CTA, 19 MB over the grid) does not depend on the previous
+  // kernel - it is requested before the dependency wait, so it lands while that kernel drains
+  int pre_n = -1;
+  if (BSTAT && p.b_pre && warp == 0 && tile_begin < tile_end) {
+    int n0, m0, s0;
+    decode(tile_begin, n0, m0, s0);
+    pre_n = n0;
+    if (elect_one()) {
+      mbar_expect_tx(bres_full, p.total_kb * Cfg::B_STAGE_BYTES);
+      for (int kb = 0, tap = 0, cblk = 0; kb < p.total_kb; ++kb) {
+        tma_load_2d(sB + kb * Cfg::B_STAGE_BYTES, &tmB, bres_full, tap * p.cin + cblk * BLOCK_K, n0 * BN);
+        if (++cblk == p.kb_per_tap) { cblk = 0; ++tap; }
+      }
+    }
+    __syncwarp();
+  }
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (elect_one()) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      int cur_n = -1;
+      int cur_n = pre_n;
       uint32_t bphase = 0;
       int tn = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      for (Walk wk = walk_begin(); walk_valid(wk); walk_next(wk)) {
+        const int tile = wk.tile;
         int n_idx, m_idx, split;
         decode(tile, n_idx, m_idx, split);
         int tx, ty, img;
@@ -238,7 +342,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int x_in0 = tx * tw * p.stride - p.pad;
         const int y_in0 = ty * p.th * p.stride - p.pad;
         int kb_begin, kb_end;
-        k_range(split, kb_begin, kb_end);
+        walk_k(wk, split, kb_begin, kb_end);
         if (BSTAT && n_idx != cur_n) {
           if (cur_n >= 0) {                       // every MMA that reads the old weights has completed
             mbar_wait(bres_empty, bphase);
@@ -297,11 +401,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int cur_n = -1;
     uint32_t bphase = 0;
     int tn = 0;
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+    for (Walk wk = walk_begin(); walk_valid(wk); walk_next(wk)) {
+      const int tile = wk.tile;
       int n_idx, m_idx, split;
       decode(tile, n_idx, m_idx, split);
       int kb_begin, kb_end;
-      k_range(split, kb_begin, kb_end);
+      walk_k(wk, split, kb_begin, kb_end);
       if (BSTAT && n_idx != cur_n) {
         cur_n = n_idx;
         mbar_wait(bres_full, bphase);
@@ -368,7 +473,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.out_f32 == nullptr && !(p.dbg & 128)) {
       const int sg = warp - 2;
       int mine = 0, gb = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      for (Walk wk = walk_begin(); walk_valid(wk); walk_next(wk)) {
+        if (SK && wk.head) continue;              // parked head: finished (and stored) by the tail owner
+        const int tile = wk.tile;
         int n_idx, m_idx, split;
         decode(tile, n_idx, m_idx, split);
         const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
@@ -378,7 +485,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       int done = 0;
       gb = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      for (Walk wk = walk_begin(); walk_valid(wk); walk_next(wk)) {
+        if (SK && wk.head) continue;
+        const int tile = wk.tile;
         int n_idx, m_idx, split;
         decode(tile, n_idx, m_idx, split);
         int tx, ty, img;
@@ -431,8 +540,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int col = bn_idx * BN + c * 64 + (gt & 63);
       bnext = (p.bias != nullptr && c * 64 < BN && col < p.cout) ? __ldg(p.bias + col) : 0.f;
     };
-    if (tile_begin < tile_end && p.out_f32 == nullptr) fetch_bias(tile_begin, 0);
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+    if (!SK && tile_begin < tile_end && p.out_f32 == nullptr) fetch_bias(tile_begin, 0);
+    for (Walk wk = walk_begin(); walk_valid(wk); walk_next(wk)) {
+      const int tile = wk.tile;
+      const bool sk_park = SK && wk.head;                 // (park) this CTA's trailing head segment, run first
+      const bool sk_fin = SK && !wk.head && wk.kb0 > 0;  // (finish) leading tail segment: add the tile parked by CTA b-1
       int n_idx, m_idx, split;
       decode(tile, n_idx, m_idx, split);
       int tx, ty, img;
@@ -459,7 +571,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          : make_uint4(0, 0, 0, 0);
         }
       };
-      if (!RES && p.resid != nullptr && c_first < nchunks) fetch_resid(c_first);
+      if (!RES && p.resid != nullptr && c_first < nchunks && !sk_park) fetch_resid(c_first);
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -468,6 +580,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       if (p.dbg & 128) {
         // experiment: no epilogue work at all (mainloop speed)
+      } else if (sk_park) {
+        // stream-K: park the fp32 accumulator tile; 32-column pieces alternate between the two groups, a warp writes
+        // 32 rows x 16 B = 512 contiguous bytes per instruction
+        float4* slot = reinterpret_cast<float4*>(p.sk_ws) + static_cast<size_t>(blockIdx.x) * (BN / 4) * BLOCK_M;
+#pragma unroll 1
+        for (int c = grp; c < BN / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld32(tbase + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            slot[(c * 8 + q) * BLOCK_M + row] =
+                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                            __uint_as_float(v[4 * q + 3]));
+          }
+        }
+        __threadfence();
+        named_bar_sync(BAR_SK, 256);
+        if (et == 0) st_release_gpu(p.sk_flags + blockIdx.x, 1u);
+        if (et == 0) trace_ev(p, 2, tn, (tile << 8) | 0xfd);     // partial tile parked
       } else if (p.out_f32 != nullptr) {
         // split-K partials: fp32, direct vector stores (GEMM view: th == 1, row index = x); 32-column pieces
         // alternate between the two groups
@@ -495,14 +627,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // the second these writes before this tile's reads.  Then start fetching the next tile's bias.
         float* gBias = sBias + grp * (BN > 128 ? BN / 2 : 64);   // each group stages its own chunks' bias: no barrier
         const int bias_key = n_idx * 2 + c_first;                // across the groups
+        if (SK && bias_key != staged_key) fetch_bias(tile, gbase);   // stream-K: no look-ahead (one key per CTA)
         if (bias_key != staged_key) {      // the weight-stationary walk keeps n_idx for many tiles: stage once
           named_bar_sync(BAR_BIAS0 + grp, 128);
           if (gt < (BN > 128 ? BN / 2 : 64)) gBias[gt] = bnext;
           named_bar_sync(BAR_BIAS0 + grp, 128);
           staged_key = bias_key;
         }
-        if (tile + tile_step < tile_end) fetch_bias(tile + tile_step, gbase + nchunks);
+        if (!SK && tile + tile_step < tile_end) fetch_bias(tile + tile_step, gbase + nchunks);
         uint8_t* buf = sOut + grp * OUT_STAGE_BYTES;
+        const float4* parked = nullptr;
+        if (sk_fin) {       // CTA b-1 parked the head part of this tile as its first item
+          const unsigned* flag = p.sk_flags + blockIdx.x - 1;
+          while (ld_acquire_gpu(flag) == 0u) {}
+          if (et == 0) trace_ev(p, 2, tn, (tile << 8) | 0xfc);   // parked tile of CTA b-1 visible
+          parked = reinterpret_cast<const float4*>(p.sk_ws) + static_cast<size_t>(blockIdx.x - 1) * (BN / 4) * BLOCK_M;
+        }
 #pragma unroll 1
         for (int c = c_first; c < nchunks; c += 2) {
           uint4 rcur[8];
@@ -514,9 +654,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[2][32];
           tmem_ld32(tbase + c * 64, v[0]);
           tmem_ld32(tbase + c * 64 + 32, v[1]);
+          float4 pk[SK ? 16 : 1];
+          if (SK && sk_fin) {                    // all 16 loads of the chunk in flight (L2 hits, written by another SM)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) pk[q] = __ldcg(parked + (c * 16 + q) * BLOCK_M + row);
+          }
           // the store warp has drained the TMA store that last read this group's staging buffer
           if (staged > 0) named_bar_sync(BAR_FREE0 + grp, 160);
           tmem_ld_wait();
+          if (SK && sk_fin) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              uint32_t* vv = &v[q >> 3][(q & 7) * 4];
+              vv[0] = __float_as_uint(__uint_as_float(vv[0]) + pk[q].x);
+              vv[1] = __float_as_uint(__uint_as_float(vv[1]) + pk[q].y);
+              vv[2] = __float_as_uint(__uint_as_float(vv[2]) + pk[q].z);
+              vv[3] = __float_as_uint(__uint_as_float(vv[3]) + pk[q].w);
+            }
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float f[32];
@@ -563,6 +718,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (et == 0) trace_ev(p, 2, tn, (tile << 8) | c);
         }
         gbase += nchunks;
+        if (sk_fin) {       // every thread has consumed its part of the parked tile: re-arm the flag for the next launch
+          named_bar_sync(BAR_SK, 256);
+          if (et == 0) st_release_gpu(p.sk_flags + blockIdx.x - 1, 0u);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -646,13 +805,35 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool BSTAT, bool RES>
+// stream-K workspace: one fp32 accumulator tile (128 x 256) + one flag per CTA.  Allocated once, outside any stream
+// capture, by conv_streamk_enable(); a single workspace serves every launch because the launches of one stream are
+// ordered (the kernel touches it only after griddepcontrol.wait) - callers that run convolutions on several streams at
+// once must switch it off.
+static float* g_sk_ws = nullptr;
+static unsigned* g_sk_flags = nullptr;
+static bool g_sk_on = false;
+
+int conv_streamk_enable(int on) {
+  if (on && g_sk_ws == nullptr) {
+    const size_t ws_bytes = static_cast<size_t>(num_sms()) * BLOCK_M * 256 * sizeof(float);
+    const size_t flag_bytes = static_cast<size_t>(num_sms() + 1) * sizeof(unsigned);
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, ws_bytes + flag_bytes) != cudaSuccess) return DVID_ERR_CUDA;
+    g_sk_ws = static_cast<float*>(ptr);
+    g_sk_flags = reinterpret_cast<unsigned*>(static_cast<uint8_t*>(ptr) + ws_bytes);
+    if (cudaMemset(g_sk_flags, 0, flag_bytes) != cudaSuccess) return DVID_ERR_CUDA;
+  }
+  g_sk_on = on != 0;
+  return 0;
+}
+
+template <int BN, bool BSTAT, bool RES, bool SK = false>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                       const ConvGemmParams& p, cudaStream_t stream) {
   using Cfg = ConvGemmCfg<BN, BSTAT, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, BSTAT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, BSTAT, RES, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return DVID_ERR_CUDA;
     attr_set = true;
@@ -664,7 +845,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     const size_t bytes = 3 * 2048 * sizeof(unsigned long long);
     cudaMalloc(&q.trace, bytes);
     cudaMemsetAsync(q.trace, 0, bytes, stream);
-    launch_pdl(conv_gemm_kernel<BN, BSTAT, RES>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, q);
+    launch_pdl(conv_gemm_kernel<BN, BSTAT, RES, SK>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, q);
     cudaStreamSynchronize(stream);
     static unsigned long long host[3 * 2048];
     cudaMemcpy(host, q.trace, bytes, cudaMemcpyDeviceToHost);
@@ -682,7 +863,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
       }
     return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
   }
-  launch_pdl(conv_gemm_kernel<BN, BSTAT, RES>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, p);
+  launch_pdl(conv_gemm_kernel<BN, BSTAT, RES, SK>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, p);
   return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
 }
 
@@ -738,6 +919,7 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     if (dbg < 0) { const char* e = getenv("DVID_DBG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
     p.trace = nullptr;
+    { const char* e = getenv("DVID_TRACE_CTA"); p.trace_cta = e ? atoi(e) : 0; }
   }
   if (out_f32 != nullptr && !(p.h_out == 1 && n == 1 && p.th == 1)) return DVID_ERR_SHAPE;  // GEMM view only
 
@@ -778,6 +960,23 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   p.div_n_tiles.init(p.n_tiles);
   p.div_tiles_x.init(p.tiles_x);
   p.div_tiles_y.init(p.tiles_y);
+  p.div_total_kb.init(p.total_kb);
+  {
+    static int wpf = -1;
+    if (wpf < 0) { const char* e = getenv("DVID_WPREFETCH"); wpf = e ? atoi(e) : 1; }
+    p.w_base = static_cast<const uint8_t*>(weight);
+    p.w_bytes = static_cast<unsigned long long>(cout) * R * S * cin * 2;
+    p.w_slice_bytes = 0;
+    { static int bpre = -1; if (bpre < 0) { const char* e = getenv("DVID_BPRE"); bpre = e ? atoi(e) : 1; } p.b_pre = bpre; }
+    if (wpf && p.w_bytes <= (8ull << 20) && (reinterpret_cast<uintptr_t>(weight) & 15) == 0) {
+      const long long total = static_cast<long long>(p.m_tiles) * p.n_tiles * p.splits;
+      const unsigned long long ctas = static_cast<unsigned long long>(total < num_sms() ? total : num_sms());
+      const unsigned long long per = (p.w_bytes + ctas - 1) / ctas;
+      p.w_slice_bytes = static_cast<unsigned>((per + 127) & ~127ull);
+    }
+  }
+  p.sk_ws = nullptr;
+  p.sk_flags = nullptr;
 
   CUtensorMap tmA, tmB, tmC;
   {
@@ -837,6 +1036,28 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   if (res_mma) {
     if (bn == 256) return launch_cfg<256, false, true>(tmA, tmB, tmC, tmR, p, stream);
     return launch_cfg<128, false, true>(tmA, tmB, tmC, tmR, p, stream);
+  }
+  {
+    // stream-K when whole-tile scheduling would waste >= 10 % of the launch (idle part of the last wave / waves): 152
+    // tiles -> 49 %, 608 -> 18 %, 2432 -> 3 % (not worth the parked-tile round trip).  tiles >= SMs keeps every CTA's
+    // range at least one tile long (a tile is shared by two CTAs at most); the flattened index must fit an int.
+    const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+    const int sms = num_sms();
+    const long long waves = (tiles + sms - 1) / sms;
+    const double idle = static_cast<double>(waves * sms - tiles) / sms;
+    static int sk_min_kb = -1;
+    static int sk_max_waves = -1;
+    if (sk_min_kb < 0) { const char* e = getenv("DVID_SK_MIN_KB"); sk_min_kb = e ? atoi(e) : 32; }
+    if (sk_max_waves < 0) { const char* e = getenv("DVID_SK_MAX_WAVES"); sk_max_waves = e ? atoi(e) : 2; }
+    if (g_sk_on && g_sk_ws != nullptr && out != nullptr && p.splits == 1 && tiles >= sms && idle >= 0.1 * waves &&
+        waves <= sk_max_waves &&
+        p.total_kb >= sk_min_kb && tiles * p.total_kb < (1LL << 30) && p.trace == nullptr && p.dbg == 0) {
+      p.sk_ws = g_sk_ws;
+      p.sk_flags = g_sk_flags;
+      if (bn == 256) return launch_cfg<256, false, false, true>(tmA, tmB, tmC, tmR, p, stream);
+      if (bn == 128) return launch_cfg<128, false, false, true>(tmA, tmB, tmC, tmR, p, stream);
+      return launch_cfg<64, false, false, true>(tmA, tmB, tmC, tmR, p, stream);
+    }
   }
   if (bn == 256) return launch_cfg<256, false, false>(tmA, tmB, tmC, tmR, p, stream);
   if (bn == 128) return launch_cfg<128, false, false>(tmA, tmB, tmC, tmR, p, stream);

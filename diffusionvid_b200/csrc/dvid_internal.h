@@ -14,6 +14,7 @@
 namespace dvid {
 
 int num_sms();
+int conv_streamk_enable(int on);   // conv_gemm.cu: allocate the stream-K workspace (outside capture) / switch it
 
 int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, const uint32_t* elem_strides);

@@ -109,6 +109,10 @@ class DiffusionDet(nn.Module):
         self.use_streams = bool(hp.get("use_streams", True))
         self.frames_per_stream = int(hp.get("frames_per_stream", 8))
         self.debug_trace = False
+        # stream-K schedule for conv layers with badly quantised tile counts (152 res4 tiles on 148 SMs).  Opt-in: on
+        # B200 it measured equal (3x3 layers) or slower (1x1 layers) than the two-wave schedule inside the pipeline
+        # (profiles/README.md).  The library has ONE workspace, so it is switched off around parallel stream branches.
+        self.streamk = bool(int(__import__("os").environ.get("DVID_STREAMK", hp.get("streamk", 0))))
         self.fused_tail = bool(hp.get("fused_tail", True))
         import os as _os
         self.extract_batch = int(_os.environ.get("DVID_EXTRACT_BATCH", hp.get("extract_batch", 32)))
@@ -524,6 +528,8 @@ class DiffusionDet(nn.Module):
         if len(fns) == 1 or torch.device(self.device).type != "cuda" or not self.use_streams:
             return [f() for f in fns]
         cur = torch.cuda.current_stream()
+        if self.streamk:
+            ops.conv_streamk(False)      # concurrent branches would share the single stream-K workspace
         streams = getattr(self, pool)
         while len(streams) < len(fns):
             # branch 0 carries the critical chain: give it scheduling priority over the helper branches
@@ -535,6 +541,8 @@ class DiffusionDet(nn.Module):
                 outs.append(f())
         for st in streams[:len(fns)]:
             cur.wait_stream(st)
+        if self.streamk:
+            ops.conv_streamk(True)
         return outs
 
     def _can_fork(self):
@@ -696,6 +704,8 @@ class DiffusionDet(nn.Module):
     def _forward_test(self, imgs, ref_l, ref_g, infos):
         hp = self.hp
         dev = torch.device(self.device)
+        if dev.type == "cuda":
+            ops.conv_streamk(self.streamk)       # process-wide library switch: set per call (several models may coexist)
         N = self.num_proposals
         ib = self.infer_batch
         if infos["frame_category"] == 0:

@@ -126,6 +126,13 @@ def gemm_partials(a, w, splits=1, out=None):
     return out, used.value
 
 
+def conv_streamk(enable):
+    """Stream-K scheduling of the conv/GEMM kernel for layers whose tile count leaves >= 1/4 of a wave idle
+    (include/dvid_b200.h, dvid_conv_streamk).  Process-wide switch; the first enable allocates the workspace and must
+    happen outside a stream capture.  Keep it off while convolutions run concurrently on several streams."""
+    check(_lib.lib().dvid_conv_streamk(1 if enable else 0), "dvid_conv_streamk")
+
+
 # ------------------------------------------------------------------------------------------------ image side
 def preprocess(img, mean, std, halo=3):
     """img [n,3,H,W] fp32 in [0,1], or uint8 as decoded (the reference's ToTensor, transforms.py:295-297, is then

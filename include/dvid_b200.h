@@ -65,6 +65,13 @@ DVID_API int dvid_stem_conv_f16(const void* in_haloed, const void* weight, const
  *   out_f32_partials[s,m,n] = sum_{k in split s} a[m,k] * w[n,k]                 (split-K; reduce with dvid_row_post)
  * K % 8 == 0, N % 8 == 0. `splits` is a request; the number actually used is returned in *splits_used (may be NULL).
  */
+/* Stream-K scheduling for dvid_conv2d_nhwc_f16 / dvid_gemm_f16 layers whose tile count leaves >= 1/4 wave idle (e.g. the
+ * 152-tile res4 convolutions on 148 SMs).  enable != 0 allocates the workspace (one fp32 accumulator tile + flag per
+ * SM, 19.4 MB) on first use - call it outside stream capture - and switches the mode on; 0 switches it off.  One
+ * workspace serves all launches, so keep it off when convolutions run concurrently on several streams.  Results are
+ * the same fp32 sums in a different association (k-blocks of a tile summed in two parts). Off by default. */
+DVID_API int dvid_conv_streamk(int enable);
+
 DVID_API int dvid_gemm_f16(const void* a, const void* w, const float* bias, const void* resid, void* out_f16,
                   float* out_f32_partials, int m, int n, int k, int relu, int splits, int* splits_used,
                   void* stream);

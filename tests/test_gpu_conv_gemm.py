@@ -182,3 +182,51 @@ def test_conv_partial_last_wave(cuda, cin, cout, R):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
     for _ in range(2):
         assert torch.equal(_conv(x, wt.view(cout, -1), bias, None, cout, R, R, 1, R // 2, 0, 1), first)
+
+
+@pytest.fixture
+def streamk():
+    L = _lib.lib()
+    _lib.check(L.dvid_conv_streamk(1), "dvid_conv_streamk")
+    yield
+    _lib.check(L.dvid_conv_streamk(0), "dvid_conv_streamk")
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,R,topdown", [
+    (8, 38, 64, 256, 256, 3, False),     # res4 conv2: 152 tiles x 36 k-blocks, BN=256
+    (8, 38, 64, 1024, 256, 1, False),    # res4 conv1: 152 tiles x 16 k-blocks
+    (8, 38, 64, 1024, 256, 1, True),     # FPN lateral4 + nearest-x2 top-down residual (epilogue residual path)
+    (8, 76, 128, 128, 128, 3, False),    # res3 conv2: 608 tiles x 18 k-blocks, BN=128 (4.1 waves)
+    (5, 37, 61, 512, 192, 3, False),     # ragged image / channel tails, BN=64 or 128
+])
+def test_conv_stream_k_schedule(cuda, streamk, n, h, w, cin, cout, R, topdown):
+    """Stream-K schedule (dvid_conv_streamk): the (tile, k-block) space is cut into one equal range per CTA, partial
+    accumulator tiles are parked in the workspace and finished by the CTA holding the tile's first k-blocks.  Must
+    match the fp32 reference like the whole-tile schedule, agree with it to fp32 re-association noise (<= 1 fp16 ulp
+    of the output scale), be repeatable, and leave the flags re-armed for the next launch."""
+    g = torch.Generator(device="cpu").manual_seed(cin + R + n)
+    x = torch.randn(n, h, w, cin, generator=g).half().to(cuda)
+    wt = (torch.randn(cout, R, R, cin, generator=g) / (cin * R * R) ** 0.5).half().to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    resid = torch.randn(n, (h + 1) // 2, (w + 1) // 2, cout, generator=g).half().to(cuda) if topdown else None
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias,
+                                     padding=R // 2)
+    if topdown:
+        ref = ref + torch.nn.functional.interpolate(resid.float().permute(0, 3, 1, 2), scale_factor=2,
+                                                    mode="nearest")[:, :, :h, :w]
+    else:
+        ref = torch.relu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    run = lambda: _conv(x, wt.view(cout, -1), bias, resid, cout, R, R, 1, R // 2, 1 if topdown else 0,
+                        0 if topdown else 1)
+    first = run()
+    assert not torch.isnan(first).any()
+    scale = max(1.0, ref.abs().max().item())
+    assert (first.float() - ref).abs().max().item() <= 2e-3 * scale
+    for _ in range(3):
+        assert torch.equal(run(), first)
+    _lib.check(_lib.lib().dvid_conv_streamk(0), "dvid_conv_streamk")
+    plain = run()
+    _lib.check(_lib.lib().dvid_conv_streamk(1), "dvid_conv_streamk")
+    assert (first.float() - plain.float()).abs().max().item() <= 1e-3 * scale
+    assert torch.equal(run(), first)

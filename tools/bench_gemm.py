@@ -45,16 +45,20 @@ def gemm_case(name, m, k, n, relu=False):
     print("%-28s %8.1f us  %7.1f TFLOP/s  %6.2f TB/s(min bytes)" % (name, us, 2.0 * m * n * k / us / 1e6, 2.0 * (m * k + n * k + m * n) / us / 1e6))
 
 
-print("DVID_DBG =", os.environ.get("DVID_DBG", "0"))
+print("DVID_DBG =", os.environ.get("DVID_DBG", "0"), " DVID_STREAMK =", os.environ.get("DVID_STREAMK", "0"))
+ops.conv_streamk(bool(int(os.environ.get("DVID_STREAMK", "0"))))
 B = 8
 conv_case("res2.conv3 64->256 +res", B, 152, 256, 64, 256, 1, 1, resid=True)
 conv_case("res2.conv2 3x3 64->64", B, 152, 256, 64, 64, 3, 1)
 conv_case("res3.conv1 512->128", B, 76, 128, 512, 128, 1, 1)
 conv_case("res3.conv3 128->512 +res", B, 76, 128, 128, 512, 1, 1, resid=True)
+conv_case("res3.conv2 3x3 128->128", B, 76, 128, 128, 128, 3, 1)
 conv_case("res4.conv1 1024->256", B, 38, 64, 1024, 256, 1, 1)
 conv_case("res4.conv2 3x3 256->256", B, 38, 64, 256, 256, 3, 1)
 conv_case("res4.conv3 256->1024 +res", B, 38, 64, 256, 1024, 1, 1, resid=True)
 conv_case("res5.conv2 3x3 512->512", B, 19, 32, 512, 512, 3, 1)
+conv_case("fpn_output4 3x3 256->256", B, 38, 64, 256, 256, 3, 1, relu=False)
+conv_case("fpn_output3 3x3 256->256", B, 76, 128, 256, 256, 3, 1, relu=False)
 gemm_case("dynamic_layer 2400x256->32768", 2400, 256, 32768)
 gemm_case("linear1 2400x256->2048", 2400, 256, 2048, relu=True)
 gemm_case("qkv 2400x256->768", 2400, 256, 768)

@@ -12,6 +12,7 @@ wt = (torch.randn(cout, R * R * cin) / (R * R * cin) ** 0.5).half().to(dev)
 b = torch.randn(cout).to(dev)
 rs = torch.randn(n, h, w, cout).half().to(dev) if resid else None
 out = torch.empty(n, h, w, cout, device=dev, dtype=torch.float16)
+ops.conv_streamk(bool(int(os.environ.get("DVID_STREAMK", "0"))))
 for _ in range(3):
     ops.conv2d(x, wt, b, cout, R, R, 1, R // 2, True, resid=rs, out=out)
 torch.cuda.synchronize()
