@@ -20,3 +20,14 @@ def t(fn, reps=20):
 print("topk_scores us", t(lambda: [ops.topk_scores(logits, boxes, N, eb, es, el, i * N) for i in range(3)]) / 3)
 print("nms us", t(lambda: ops.nms(eb, es, el, thr=0.5, clip_wh=(1000., 600.))))
 print("topk_mask us", t(lambda: ops.topk_mask(logits, 75, 25)))
+# fused head tail (cls / reg towers + predictors + apply_deltas), M = 2400
+M = B * N
+mk = lambda n: (torch.randn(n, 256, generator=g) / 16).half().to(dev)
+ln = lambda: ((1 + 0.1 * torch.randn(256, generator=g)).to(dev), (0.1 * torch.randn(256, generator=g)).to(dev))
+fc = torch.randn(M, 256, generator=g).half().to(dev)
+cls = (mk(256), ln()); reg = [(mk(256), ln()) for _ in range(3)]
+lw = torch.zeros(32, 256).half(); lw[:C] = (torch.randn(C, 256, generator=g) / 16).half(); lw = lw.to(dev)
+dw = torch.zeros(16, 256).half(); dw[:4] = (torch.randn(4, 256, generator=g) / 64).half(); dw = dw.to(dev)
+lb = (0.1 * torch.randn(C, generator=g)).to(dev); db = (0.1 * torch.randn(4, generator=g)).to(dev)
+bx = boxes.reshape(M, 4).contiguous()
+print("head_tail us", t(lambda: ops.head_tail(fc, cls, reg, lw, lb, C, dw, db, bx)))
