@@ -31,3 +31,12 @@ dw = torch.zeros(16, 256).half(); dw[:4] = (torch.randn(4, 256, generator=g) / 6
 lb = (0.1 * torch.randn(C, generator=g)).to(dev); db = (0.1 * torch.randn(4, generator=g)).to(dev)
 bx = boxes.reshape(M, 4).contiguous()
 print("head_tail us", t(lambda: ops.head_tail(fc, cls, reg, lw, lb, C, dw, db, bx)))
+# farthest point sampling of the global memory (diffusion_det.py:841-896): 1800 -> 900 and 600 -> 150 candidates
+for n, mm in ((1800, 900), (600, 150)):
+    feats = torch.randn(n, 256, generator=g).to(dev)
+    dist = ops.cdist(feats)
+    idx = torch.empty((1, mm), device=dev, dtype=torch.int32)
+    def run():
+        temp = torch.full((1, n), 1e10, device=dev)
+        ops.furthest_point_sampling(1, n, mm, dist, temp, idx)
+    print("fps %d->%d us" % (n, mm), t(run, reps=5))
