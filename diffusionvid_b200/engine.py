@@ -124,8 +124,11 @@ def save_predictions(predictions, output_folder, name="predictions.pth"):
     return path
 
 
-def inference(model, data_loader, device="cuda", output_folder=None, timer=None):
-    """inference.py:119-168 up to the artefact (the AP evaluator is dataset tooling, out of scope)."""
+def inference(model, data_loader, device="cuda", output_folder=None, timer=None, evaluate=False, logger=None):
+    """inference.py:119-168: run the loader, gather on rank 0, write predictions.pth and - with `evaluate` and a
+    dataset that carries ground truth (get_img_info / get_groundtruth / map_class_id_to_class_name) - the VID AP50 /
+    CorLoc report of data/datasets/evaluation/vid/vid_eval.py (diffusionvid_b200/evaluation.py).  Returns the
+    prediction list, or (predictions, metrics) when evaluating."""
     device = torch.device(device)
     predictions = compute_on_dataset(model, data_loader, device, timer)
     if dist.is_available() and dist.is_initialized():
@@ -135,4 +138,7 @@ def inference(model, data_loader, device="cuda", output_folder=None, timer=None)
         return None
     if output_folder:
         save_predictions(predictions, output_folder)
+    if evaluate:
+        from . import evaluation
+        return predictions, evaluation.do_vid_evaluation(data_loader.dataset, predictions, output_folder, logger)
     return predictions
