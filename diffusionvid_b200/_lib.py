@@ -18,7 +18,7 @@ I = ctypes.c_int
 L = ctypes.c_long
 F = ctypes.c_float
 
-# name -> argtypes; every entry point returns int.  Kept in the order of include/dvid_b200.h.
+# name -> argtypes; every entry point returns int (dvid_resize_workspace_bytes: long).  Kept in the order of include/dvid_b200.h.
 SIGNATURES = {
     "dvid_abi_version": [],
     "dvid_conv_streamk": [I],
@@ -49,6 +49,8 @@ SIGNATURES = {
     "dvid_swin_patch_merge": [P, I, I, I, I, P, P, P, P],
     "dvid_swin_patch_gather": [P, P, I, I, I, P, P, P],
     "dvid_swin_patch_gather_u8": [P, P, I, I, I, P, P, P],
+    "dvid_resize_workspace_bytes": [I, I, I, I, I],
+    "dvid_resize_bilinear_u8": [P, I, I, I, I, I, P, I, I, P, L, P],
     "dvid_swin_window_attention": [P, P, P, I, I, I, I, I, I, P],
 }
 
@@ -69,7 +71,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(cdll, name)      # AttributeError here = header / library mismatch: fail loudly
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_int
+            fn.restype = ctypes.c_long if name == "dvid_resize_workspace_bytes" else ctypes.c_int
         _lib = cdll
     return _lib
 

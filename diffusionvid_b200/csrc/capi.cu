@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 8
+#define DVID_ABI_VERSION 9
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -48,6 +48,18 @@ int dvid_preprocess(const float* img, void* out, int n, int H, int W, int halo, 
                     const float* std, void* stream) {
   if (!img || !out || !mean || !std) return DVID_ERR_ARG;
   return dvid::preprocess_launch(img, 0, out, n, H, W, halo, Hp, Wp, mean, std, S(stream));
+}
+
+long dvid_resize_workspace_bytes(int n, int Hin, int Win, int oh, int ow) {
+  return dvid::resize_workspace_bytes(n, Hin, Win, oh, ow);
+}
+
+int dvid_resize_bilinear_u8(const unsigned char* src_hwc, int n, int Hin, int Win, int oh, int ow,
+                            unsigned char* dst_chw, int Hp, int Wp, void* workspace, long workspace_bytes,
+                            void* stream) {
+  if (!src_hwc || !dst_chw || !workspace) return DVID_ERR_ARG;
+  return dvid::resize_bilinear_u8_launch(src_hwc, n, Hin, Win, oh, ow, dst_chw, Hp, Wp, workspace, workspace_bytes,
+                                         S(stream));
 }
 
 int dvid_preprocess_u8(const unsigned char* img, void* out, int n, int H, int W, int halo, int Hp, int Wp,

@@ -40,6 +40,9 @@ int roi_dynconv_launch(const void* const* feats, const int* hs, const int* ws, c
 
 int preprocess_launch(const void* img, int is_u8, void* out, int n, int H, int W, int halo, int Hp, int Wp,
                       const float* mean, const float* std, cudaStream_t stream);
+long resize_workspace_bytes(int n, int Hin, int Win, int oh, int ow);
+int resize_bilinear_u8_launch(const unsigned char* src, int n, int Hin, int Win, int oh, int ow, unsigned char* dst,
+                              int Hp, int Wp, void* workspace, long workspace_bytes, cudaStream_t stream);
 int maxpool_launch(const void* in, void* out, int n, int H, int W, int C, cudaStream_t stream);
 int row_post_launch(const float* partials, int splits, long split_stride, const void* in_f16, const float* bias,
                     const float* ln1_g, const float* ln1_b, int relu1, const float* resid, const float* ln2_g,

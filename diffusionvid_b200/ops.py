@@ -149,6 +149,27 @@ def preprocess(img, mean, std, halo=3):
     return out
 
 
+def resize_frames_u8(frames_hwc, oh, ow, pad_to=32):
+    """Decoded frames [n, Hin, Win, 3] uint8 (PIL order) -> [n, 3, Hp, Wp] uint8, the Pillow-bilinear resize of the
+    reference's test transform (transforms.py:31-67) in the top-left oh x ow corner, zero padding up to a multiple of
+    `pad_to` (to_image_list).  Bytes equal Pillow's (dvid_resize_bilinear_u8)."""
+    _chk(frames_hwc, torch.uint8, "frames_hwc")
+    n, hin, win, c = frames_hwc.shape
+    if c != 3:
+        raise _lib.DvidError("frames_hwc: expected [n, H, W, 3]")
+    hp = (oh + pad_to - 1) // pad_to * pad_to if pad_to > 0 else oh
+    wp = (ow + pad_to - 1) // pad_to * pad_to if pad_to > 0 else ow
+    need = _lib.lib().dvid_resize_workspace_bytes(n, hin, win, oh, ow)
+    if need < 0:
+        raise _lib.DvidError("dvid_resize_workspace_bytes: bad shape")
+    ws = torch.empty((need,), device=frames_hwc.device, dtype=torch.uint8)
+    out = torch.empty((n, 3, hp, wp), device=frames_hwc.device, dtype=torch.uint8)
+    check(_lib.lib().dvid_resize_bilinear_u8(ptr(frames_hwc), n, hin, win, oh, ow, ptr(out), hp, wp, ptr(ws), need,
+                                             cur_stream()), "dvid_resize_bilinear_u8")
+    _cnt(4)
+    return out
+
+
 def maxpool3x3s2(x):
     _chk(x, H, "x")
     n, h, w, c = x.shape

@@ -213,6 +213,16 @@ DVID_API int dvid_swin_patch_merge(const float* x, int B, int H, int W, int C, c
  * out_f16 [B*(H/4)*(W/4)][64], k = c*16 + py*4 + px, k >= 48 zero.  mean/std: 3 host floats (already / 255). */
 DVID_API int dvid_swin_patch_gather(const float* img, void* out_f16, int B, int H, int W, const float* mean,
                            const float* std, void* stream);
+/* Clip loader, first stage: the reference's test-time Resize (mega_core/data/transforms/transforms.py:31-67 ->
+ * torchvision F.resize on a PIL image = Pillow Image.resize(BILINEAR): antialiased two-pass triangle filter in 22-bit
+ * fixed point, libImaging/Resample.c) on decoded frames.  src_hwc [n][Hin][Win][3] uint8 -> dst_chw [n][3][Hp][Wp]
+ * uint8 with the oh x ow result in the top-left corner and zeros elsewhere (the padding to_image_list adds,
+ * structures/image_list.py:36-66).  Output bytes equal Pillow's.  `workspace`: device scratch of at least
+ * dvid_resize_workspace_bytes(...) bytes (horizontal-pass image + coefficient tables, computed on the device). */
+DVID_API long dvid_resize_workspace_bytes(int n, int Hin, int Win, int oh, int ow);
+DVID_API int dvid_resize_bilinear_u8(const unsigned char* src_hwc, int n, int Hin, int Win, int oh, int ow,
+                            unsigned char* dst_chw, int Hp, int Wp, void* workspace, long workspace_bytes,
+                            void* stream);
 /* uint8 frames (ToTensor fused, see dvid_preprocess_u8); W % 4 == 0 keeps the 4-pixel loads aligned. */
 DVID_API int dvid_swin_patch_gather_u8(const unsigned char* img, void* out_f16, int B, int H, int W, const float* mean,
                               const float* std, void* stream);

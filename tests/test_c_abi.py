@@ -18,7 +18,7 @@ def _declarations():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)          # drop comments
     decls = {}
-    for m in re.finditer(r"DVID_API\s+int\s+(\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"DVID_API\s+(?:int|long)\s+(\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
         decls[m.group(1)] = (n, args)
@@ -41,7 +41,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in _declarations():
         assert hasattr(lib, name), "header declares %s but the library does not export it" % name
     lib.dvid_abi_version.restype = ctypes.c_int
-    assert lib.dvid_abi_version() >= 8
+    assert lib.dvid_abi_version() >= 9
 
 
 def test_binding_table_matches_the_header():

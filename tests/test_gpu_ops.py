@@ -428,3 +428,44 @@ def test_fused_head_tail_matches_layerwise_math(cuda, M):
     assert lg.shape == (M, C) and bx.shape == (M, 4)
     assert (lg.cpu() - ref_lg).abs().max().item() <= 5e-3
     assert (bx.cpu() - ref_bx).abs().max().item() <= 5e-3 * 500
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(72, 128, 56, 100), (90, 160, 75, 133), (60, 100, 60, 100), (50, 80, 75, 120),
+                                       (97, 131, 40, 131), (33, 47, 99, 20), (720, 1280, 562, 999)])
+def test_resize_bilinear_u8_equals_pillow_restatement(cuda, h, w, oh, ow):
+    """dvid_resize_bilinear_u8 vs oracle/resize.py (Pillow's 8-bit antialiased bilinear resample, pinned against the
+    installed Pillow in tests/test_oracle_resize.py): the same BYTES - down-, up-scaling, identity and mixed axes, the
+    720p -> 562x999 case of the VID frames - plus planar layout and zero padding to a multiple of 32."""
+    from oracle import resize as orz
+    rng = np.random.default_rng(h * 1000 + w)
+    n = 2
+    img = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    img[:, : h // 4] = 255; img[:, h // 4: h // 2, : w // 2] = 0
+    got = ops.resize_frames_u8(torch.from_numpy(img).to(cuda), oh, ow, pad_to=32).cpu().numpy()
+    hp, wp = (oh + 31) // 32 * 32, (ow + 31) // 32 * 32
+    assert got.shape == (n, 3, hp, wp)
+    for i in range(n):
+        want = orz.resize_bilinear_u8(img[i], oh, ow)
+        assert np.array_equal(got[i, :, :oh, :ow], want.transpose(2, 0, 1))
+    assert got[:, :, oh:, :].sum() == 0 and got[:, :, :, ow:].sum() == 0
+
+
+def test_gpu_frame_transform_feeds_the_uint8_entry(cuda):
+    """GpuFrameTransform = Resize(600, 1000) + ToTensor + to_image_list(32) of the reference's test pipeline on decoded
+    frames: sizes by Resize.get_size, bytes by Pillow's resample, then dvid_preprocess_u8 == to_tensor + normalizer."""
+    from diffusionvid_b200 import clip_loader
+    from oracle import resize as orz
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, size=(2, 180, 320, 3), dtype=np.uint8)
+    t = clip_loader.GpuFrameTransform(min_size=150, max_size=250, size_divisible=32)
+    il = t(torch.from_numpy(frames).pin_memory())
+    oh, ow = orz.get_size((320, 180), 150, 250)
+    assert (oh, ow) == (141, 250) and il.image_sizes == [(oh, ow)] * 2 and il.tensors.shape == (2, 3, 160, 256)
+    assert il.tensors.dtype == torch.uint8 and il.tensors.is_cuda and t.h2d_bytes == frames.size
+    want = np.stack([orz.resize_bilinear_u8(f, oh, ow).transpose(2, 0, 1) for f in frames])
+    assert np.array_equal(il.tensors[:, :, :oh, :ow].cpu().numpy(), want)
+    mean = [123.675 / 255, 116.28 / 255, 103.53 / 255]; std = [58.395 / 255, 57.12 / 255, 57.375 / 255]
+    a = ops.preprocess(il.tensors, mean, std, halo=3)
+    ref = torch.zeros(2, 3, 160, 256); ref[:, :, :oh, :ow] = torch.from_numpy(want).float().div(255)
+    b = ops.preprocess(ref.to(cuda), mean, std, halo=3)
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
