@@ -333,6 +333,15 @@ def run_ours(args):
                     "top_shapes": [{"shape": k.split(":", 1)[1], "launches": n, "ms": round(t, 3),
                                     "tflops": round(fl / t / 1e9, 1) if t > 0 else 0.0}
                                    for t, k, n, fl in sorted(shapes, reverse=True)[:8]]}
+            rd = fam.get("roi_dynconv")
+            if rd and peak_bw:
+                # the fused ROIAlign + DynamicConv step against the HBM roofline (north_star): algorithmic bytes per box
+                # = generated weights in (64 KB) + ROI-tile-equivalent of feature reads and the 49x256 result (2 x 25 KB)
+                roof["decoder_step"] = {"kernel": "roi_dynconv_kernel (fused ROIAlign + DynamicConv bmm/LN)",
+                                        "bound": "hbm", "achieved": rd["gbs"], "peak": peak_bw, "unit": "GB/s",
+                                        "frac": rd["gbs"] / peak_bw, "launches_per_step": rd["launches"],
+                                        "avg_launch_us": 1000.0 * rd["ms"] / max(1, rd["launches"]),
+                                        "share_of_step": rd["ms"] / clip_ms if clip_ms > 0 else None}
             tf = os.path.join(ROOT, "profiles", "conv_gemm_traffic.json")
             if os.path.exists(tf):       # dram bytes per launch from the committed ncu --set full capture
                 with open(tf) as f:

@@ -197,3 +197,28 @@ def test_uint8_frames_equal_fp32_frames(cuda):
     assert sent[0] == 4 * sent[1] and sent[1] >= (L + 4) * 3 * h * w and sent[1] % (3 * h * w) == 0
     for (b0, s0, l0), (b1, s1, l1) in zip(*outs):
         assert torch.equal(b0, b1) and torch.equal(s0, s1) and torch.equal(l0, l1)
+
+
+def test_stream_k_schedule_inside_the_model(cuda):
+    """Opt-in stream-K schedule (hp streamk=1 / DVID_STREAMK=1): at 600x1000 the res4 3x3 convolutions of an 8-frame
+    batch are 152 tiles on 148 SMs and take the stream-K variant inside the captured extract unit; the library switch
+    is toggled around parallel stream branches.  Detections must agree with the default schedule to fp16 noise (the
+    k-blocks of a shared tile are summed in two parts) and the switch must be off again for the next model."""
+    h, w, L = 600, 1000, 9
+    outs = []
+    for sk in (0, 1):
+        hp, sd, m, noise, ocfg = _models(1, hp_over=dict(streamk=sk, num_proposals=100))
+        frames = synth.make_clip(L, h, w, seed=6).to(cuda)
+        res = []
+        for s in synth.clip_samples(frames, [3, 7], h, w):
+            got = m(dict(cur=structures.ImageList(s["cur"], [(h, w)]),
+                         ref_l=[structures.ImageList(t, [(h, w)]) for t in s["ref_l"]],
+                         ref_g=[structures.ImageList(t, [(h, w)]) for t in s["ref_g"]],
+                         frame_id=s["frame_id"], start_id=0, end_id=s["end_id"], seg_len=L,
+                         frame_category=s["frame_category"], video_id=0))
+            res += [(b.bbox.cpu(), b.get_field("scores").cpu(), b.get_field("labels").cpu()) for b in got]
+        outs.append(res)
+    assert len(outs[0]) == len(outs[1]) == L
+    fracs = sorted(match_fraction(b1, s1, l1, b0, s0, l0, max(h, w), box_tol=2e-3, score_tol=4e-3)
+                   for (b0, s0, l0), (b1, s1, l1) in zip(*outs))
+    assert fracs[len(fracs) // 2] >= 0.95, fracs
