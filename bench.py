@@ -9,7 +9,11 @@ reference frames at the video start (backbone + 3 base stages on all 88 frames, 
 
   value : frames/s with the clip's images already resident in HBM when the timed region starts.
   e2e   : the same clip fed from pinned HOST memory (H2D copies of every ref frame inside the timed region) and the
-          detections read back to the host (D2H) - the number to compare with the reference arm.
+          detections read back to the host (D2H) - the number to compare with the reference arm.  The loop is the
+          reference's (engine/inference.py:66-78): call, move the outputs to the CPU, store; the model's host-result
+          BoxLists are deferred (they wait for their asynchronous D2H copy on first access), so the host runs ahead and
+          the next batch's frame uploads overlap the current batch's compute; every detection is read on the host
+          before the timed region ends.
   e2e_u8: the same call fed with the frames as decoded 8-bit images (uint8 ImageLists; SURVEY.md 8f-1 clip loader):
           the reference's ToTensor is evaluated by the first GPU kernel, a quarter of the bytes cross PCIe.
   roofline : the dominant kernel family (tcgen05 conv/GEMM), algorithmic FLOPs / CUDA-event time measured live in a
@@ -207,15 +211,22 @@ def make_clip_inputs(args, dev, pinned, u8=False):
 
 
 def run_clip(model, samples, to_host):
+    """One clip through the public call, driven like mega_core/engine/inference.py:66-78 drives the reference: every
+    output is moved to the CPU right after the call and stored; the detections are then all read on the host (still
+    inside the caller's timed region)."""
     n_out = 0
     d2h = 0
+    kept = []
     for s in samples:
         out = model(s)
         if to_host:
-            for bl in out:
-                b = bl.bbox.cpu(); sc = bl.get_field("scores").cpu(); lb = bl.get_field("labels").cpu()
-                d2h += b.numel() * 4 + sc.numel() * 4 + lb.numel() * 8
+            kept.append([o.to("cpu") for o in out])
         n_out += len(out)
+    for out in kept:
+        for bl in out:
+            b = bl.bbox; sc = bl.get_field("scores"); lb = bl.get_field("labels")
+            assert not b.is_cuda and b.shape[0] == sc.shape[0] == lb.shape[0]
+            d2h += b.numel() * 4 + sc.numel() * 4 + lb.numel() * 8
     return n_out, d2h
 
 

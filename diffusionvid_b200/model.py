@@ -133,7 +133,9 @@ class DiffusionDet(nn.Module):
         self._streams_inner = []
         self._copy_stream = None
         self.io_bytes = {"h2d": 0, "d2h": 0}   # bytes moved by the model itself (bench.py reports them)
-        self._host_buf = None
+        self._host_ring = [None] * 4          # pinned result buffers of the last key batches (host_results mode)
+        self._host_ring_pos = 0
+        self.deferred_results = bool(int(_os.environ.get("DVID_DEFERRED_RESULTS", hp.get("deferred_results", 1))))
         self.host_results = bool(hp.get("host_results", False))
         self._shard = None
         self.eval()
@@ -910,23 +912,31 @@ class DiffusionDet(nn.Module):
 
     def _results_on_host(self, r, batch, cap, w, h):
         """`host_results` mode: ONE device->host copy per key batch (count | boxes | scores | labels packed in fp32; counts
-        <= cap and labels <= 30 are exact) into pinned memory, BoxLists built from CPU views.  The reference's engine
-        moves every BoxList to the CPU right after the call anyway (mega_core/engine/inference.py:75)."""
+        <= cap and labels <= 30 are exact) into pinned memory.  The call does not wait for it: the BoxLists are deferred
+        (structures.BoxList.deferred) and wait for the copy's event on first access.  The reference's engine only moves
+        every BoxList to the CPU right after the call and stores it (mega_core/engine/inference.py:75-78), so under that
+        loop the host runs ahead, the uploads of the NEXT key batch's frames (which arrive in the following calls)
+        overlap this batch's compute, and the GPU never idles between key batches; a caller that reads a result
+        immediately blocks exactly as it did with the synchronous copy.  `deferred_results = False` restores that."""
         packed = torch.cat([r["count"].to(F32).view(batch, 1), r["boxes"].reshape(batch, -1), r["scores"],
                             r["labels"].to(F32)], dim=1)
-        if self._host_buf is None or self._host_buf.shape != packed.shape:
-            self._host_buf = torch.empty(packed.shape, dtype=F32, pin_memory=True)
-        self._host_buf.copy_(packed, non_blocking=True)
+        slot = self._host_ring_pos % len(self._host_ring)
+        self._host_ring_pos += 1
+        old = self._host_ring[slot]
+        if old is not None:
+            old[1].resolve()          # the pinned buffer is about to be reused: its batch (long complete) moves out
+        buf = old[0] if old is not None and old[0].shape == packed.shape else \
+            torch.empty(packed.shape, dtype=F32, pin_memory=True)
+        buf.copy_(packed, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
         self.io_bytes["d2h"] += packed.numel() * 4
-        torch.cuda.current_stream().synchronize()
-        hb = self._host_buf.clone()
-        results = []
-        for i in range(batch):
-            c = int(hb[i, 0].item())
-            bl = BoxList(hb[i, 1:1 + 4 * cap].view(cap, 4)[:c], (w, h), mode="xyxy")
-            bl.add_field("scores", hb[i, 1 + 4 * cap:1 + 5 * cap][:c])
-            bl.add_field("labels", hb[i, 1 + 5 * cap:1 + 6 * cap][:c].long())
-            results.append(bl)
+        pend = _PendingBatch(buf, ev, batch, cap)
+        self._host_ring[slot] = (buf, pend)
+        results = [BoxList.deferred((lambda i=i: pend.frame(i)), (w, h), mode="xyxy") for i in range(batch)]
+        if not self.deferred_results:
+            for bl in results:
+                bl._materialize()
         return results
 
     # ------------------------------------------------------------------------------------------ frame sharding
@@ -985,6 +995,27 @@ class DiffusionDet(nn.Module):
 
     def _graph_active(self):
         return self.use_graphs and torch.device(self.device).type == "cuda"
+
+
+class _PendingBatch:
+    """Detections of one key batch on their way to the host: pinned buffer + the event recorded behind the copy."""
+
+    def __init__(self, buf, event, batch, cap):
+        self.buf, self.event, self.batch, self.cap = buf, event, batch, cap
+        self.host = None
+
+    def resolve(self):
+        if self.host is None:
+            self.event.synchronize()
+            self.host = self.buf.clone()      # pageable copy: the pinned buffer goes back to the ring
+            self.buf = None
+        return self.host
+
+    def frame(self, i):
+        hb, cap = self.resolve(), self.cap
+        c = int(hb[i, 0].item())
+        return (hb[i, 1:1 + 4 * cap].view(cap, 4)[:c],
+                {"scores": hb[i, 1 + 4 * cap:1 + 5 * cap][:c], "labels": hb[i, 1 + 5 * cap:1 + 6 * cap][:c].long()})
 
 
 class _CapturedUnit:

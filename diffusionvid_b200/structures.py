@@ -23,10 +23,65 @@ class BoxList(object):
             raise ValueError("last dimension of bbox should have a size of 4, got {}".format(bbox.size(-1)))
         if mode not in ("xyxy", "xywh"):
             raise ValueError("mode should be 'xyxy' or 'xywh'")
-        self.bbox = bbox
+        self._bbox = bbox
+        self._fields = {}
+        self._pending = None
         self.size = image_size   # (image_width, image_height)
         self.mode = mode
-        self.extra_fields = {}
+
+    # ---- deferred results
+    # The model's `host_results` mode returns BoxLists whose tensors are still in flight (an asynchronous device->host
+    # copy of the key batch).  `resolver()` waits for that copy and returns (bbox, {field: tensor}); it runs on the first
+    # access to the boxes, a field or the length, so a caller that only stores the result - like the reference's loop,
+    # `output = [o.to(cpu_device) for o in output]; results_dict.update(...)` (mega_core/engine/inference.py:75-78) - never
+    # blocks on the GPU, and a caller that looks at it immediately gets the same values as before.
+    @classmethod
+    def deferred(cls, resolver, image_size, mode="xyxy"):
+        self = cls.__new__(cls)
+        self._bbox = None
+        self._fields = {}
+        self._pending = resolver
+        self.size = image_size
+        self.mode = mode
+        return self
+
+    def _materialize(self):
+        if self._pending is not None:
+            resolver, self._pending = self._pending, None
+            bbox, fields = resolver()
+            self._bbox = bbox
+            for k, v in fields.items():
+                self._fields.setdefault(k, v)
+
+    @property
+    def is_pending(self):
+        return self._pending is not None
+
+    @property
+    def bbox(self):
+        self._materialize()
+        return self._bbox
+
+    @bbox.setter
+    def bbox(self, value):
+        self._materialize()
+        self._bbox = value
+
+    @property
+    def extra_fields(self):
+        self._materialize()
+        return self._fields
+
+    def __getstate__(self):      # pickled like the reference's BoxList: bbox / size / mode / extra_fields
+        self._materialize()
+        return {"bbox": self._bbox, "size": self.size, "mode": self.mode, "extra_fields": self._fields}
+
+    def __setstate__(self, state):
+        self._bbox = state["bbox"]
+        self._fields = state.get("extra_fields", {})
+        self._pending = None
+        self.size = state["size"]
+        self.mode = state["mode"]
 
     # ---- fields
     def add_field(self, field, field_data):
@@ -94,6 +149,8 @@ class BoxList(object):
 
     # ---- container protocol
     def to(self, device):
+        if self._pending is not None and torch.device(device).type == "cpu":
+            return self          # deferred results land in host memory: nothing to move, nothing to wait for
         out = BoxList(self.bbox.to(device), self.size, self.mode)
         for k, v in self.extra_fields.items():
             out.add_field(k, v.to(device) if hasattr(v, "to") else v)

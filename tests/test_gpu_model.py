@@ -222,3 +222,38 @@ def test_stream_k_schedule_inside_the_model(cuda):
     fracs = sorted(match_fraction(b1, s1, l1, b0, s0, l0, max(h, w), box_tol=2e-3, score_tol=4e-3)
                    for (b0, s0, l0), (b1, s1, l1) in zip(*outs))
     assert fracs[len(fracs) // 2] >= 0.95, fracs
+
+
+def test_deferred_host_results_equal_synchronous_ones(cuda):
+    """host_results mode returns BoxLists that wait for their asynchronous device->host copy on first access
+    (structures.BoxList.deferred): the call itself does not block, `.to("cpu")` does not block (the reference loop,
+    engine/inference.py:75), a read blocks and yields exactly the detections of the synchronous copy; results stay
+    valid after the pinned ring buffer has been reused by later batches."""
+    h, w, L = 192, 256, 43                      # 6 key batches: the 4-deep ring of pinned buffers wraps
+    outs = []
+    for deferred in (False, True):
+        hp, sd, m, noise, ocfg = _models(1)
+        m.host_results = True
+        m.deferred_results = deferred
+        frames = synth.make_clip(L, h, w, seed=6).pin_memory()
+        kept = []
+        for s in synth.clip_samples(frames, [17, 3, 9, 12], h, w):
+            got = m(dict(cur=structures.ImageList(s["cur"], [(h, w)]),
+                         ref_l=[structures.ImageList(t, [(h, w)]) for t in s["ref_l"]],
+                         ref_g=[structures.ImageList(t, [(h, w)]) for t in s["ref_g"]],
+                         frame_id=s["frame_id"], start_id=0, end_id=s["end_id"], seg_len=L,
+                         frame_category=s["frame_category"], video_id=0))
+            if got:
+                assert all(g.is_pending == deferred for g in got)
+                moved = [g.to("cpu") for g in got]
+                assert all(a is b for a, b in zip(moved, got)) or not deferred
+                kept += moved
+        assert len(kept) == L
+        res = [(b.bbox.clone(), b.get_field("scores").clone(), b.get_field("labels").clone()) for b in kept]
+        assert all(not b.is_pending and not b.bbox.is_cuda and len(b) == b.get_field("scores").numel() for b in kept)
+        outs.append(res)
+    for (b0, s0, l0), (b1, s1, l1) in zip(*outs):
+        assert torch.equal(b0, b1) and torch.equal(s0, s1) and torch.equal(l0, l1)
+    import pickle
+    back = pickle.loads(pickle.dumps(kept[0]))
+    assert torch.equal(back.bbox, kept[0].bbox) and back.size == kept[0].size and back.fields() == kept[0].fields()
