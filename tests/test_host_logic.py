@@ -207,6 +207,32 @@ def test_uint8_frames_follow_the_fp32_protocol(shim):
         assert torch.equal(b0, b1) and torch.equal(s0, s1) and torch.equal(l0, l1)
 
 
+def test_deferred_boxlist_resolves_on_first_access():
+    """BoxList.deferred (host_results mode of the model): storing or `.to("cpu")` does not resolve, any read does -
+    once - and the object then behaves and pickles like a plain BoxList (bbox / size / mode / extra_fields, the layout
+    of the reference's class, structures/bounding_box.py:9-40)."""
+    BoxList = structures.BoxList
+    calls = []
+
+    def resolver():
+        calls.append(1)
+        return (torch.tensor([[1., 2., 30., 40.], [5., 6., 7., 8.]]),
+                {"scores": torch.tensor([0.9, 0.1]), "labels": torch.tensor([3, 7])})
+    b = BoxList.deferred(resolver, (100, 50))
+    assert b.is_pending and b.to("cpu") is b and b.size == (100, 50) and b.mode == "xyxy" and not calls
+    assert len(b) == 2 and calls == [1] and not b.is_pending
+    assert b.fields() == ["scores", "labels"] and b.get_field("labels").tolist() == [3, 7]
+    assert len(b[torch.tensor([True, False])]) == 1 and b.resize((200, 100)).bbox[0, 2].item() == 60.0
+    assert calls == [1]
+    c = pickle.loads(pickle.dumps(BoxList.deferred(resolver, (100, 50))))
+    assert calls == [1, 1] and torch.equal(c.bbox, b.bbox) and c.get_field("scores").tolist() == b.get_field("scores").tolist()
+    state = b.__getstate__()
+    assert set(state) == {"bbox", "size", "mode", "extra_fields"}
+    d = BoxList.deferred(resolver, (100, 50))
+    d.add_field("extra", torch.tensor([1, 2]))          # writing a field resolves first, then adds
+    assert d.fields() == ["scores", "labels", "extra"]
+
+
 def test_package_exports():
     assert diffusionvid_b200.__version__
     assert hasattr(diffusionvid_b200, "build_detection_model")
