@@ -135,6 +135,8 @@ class DiffusionDet(nn.Module):
         self.io_bytes = {"h2d": 0, "d2h": 0}   # bytes moved by the model itself (bench.py reports them)
         self._host_ring = [None] * 4          # pinned result buffers of the last key batches (host_results mode)
         self._host_ring_pos = 0
+        self._dev_ring = [None] * 4           # device-resident results whose counts have not been read yet
+        self._dev_ring_pos = 0
         self.deferred_results = bool(int(_os.environ.get("DVID_DEFERRED_RESULTS", hp.get("deferred_results", 1))))
         self.host_results = bool(hp.get("host_results", False))
         self._shard = None
@@ -836,18 +838,25 @@ class DiffusionDet(nn.Module):
             r = self._exchange_results(r, own, batch, cap, dev)
         if self.host_results and dev.type == "cuda":
             return self._results_on_host(r, batch, cap, w, h)
-        counts = r["count"].cpu().tolist()       # the one device->host read of the batch
+        # Device-resident results: the per-frame detection counts are the one device->host read of the batch, and it
+        # is deferred too (BoxList.deferred): a caller that keeps the detections on the GPU or looks at them later does
+        # not stall the launch of the next key batch (0.13 ms of GPU idle per batch with the synchronous read).  The
+        # 4-deep ring resolves the oldest batch before its slot is reused, which bounds how far the host runs ahead.
+        cnt, ob, osc, ol = r["count"], r["boxes"], r["scores"], r["labels"]
+        if self._graph_active() and world == 1:       # graph-owned buffers: the next replay overwrites them
+            cnt, ob, osc, ol = cnt.clone(), ob.clone(), osc.clone(), ol.clone()
         self.io_bytes["d2h"] += 4 * batch
-        ob, osc, ol = r["boxes"], r["scores"], r["labels"]
-        if self._graph_active() and world == 1:
-            ob, osc, ol = ob.clone(), osc.clone(), ol.clone()
-        results = []
-        for i in range(batch):
-            c = int(counts[i])
-            bl = BoxList(ob[i, :c], (w, h), mode="xyxy")
-            bl.add_field("scores", osc[i, :c])
-            bl.add_field("labels", ol[i, :c].long())
-            results.append(bl)
+        pend = _PendingDeviceBatch(cnt, ob, osc, ol)
+        slot = self._dev_ring_pos % len(self._dev_ring)
+        self._dev_ring_pos += 1
+        if self._dev_ring[slot] is not None:
+            self._dev_ring[slot].resolve()
+        self._dev_ring[slot] = pend
+        results = [BoxList.deferred((lambda i=i: pend.frame(i)), (w, h), mode="xyxy", on_host=False)
+                   for i in range(batch)]
+        if not self.deferred_results or dev.type != "cuda":
+            for bl in results:
+                bl._materialize()
         return results
 
     # ------------------------------------------------------------------------------------------ upload pipeline
@@ -1016,6 +1025,23 @@ class _PendingBatch:
         c = int(hb[i, 0].item())
         return (hb[i, 1:1 + 4 * cap].view(cap, 4)[:c],
                 {"scores": hb[i, 1 + 4 * cap:1 + 5 * cap][:c], "labels": hb[i, 1 + 5 * cap:1 + 6 * cap][:c].long()})
+
+
+class _PendingDeviceBatch:
+    """Detections of one key batch that stay on the device; only the per-frame counts go to the host, on demand."""
+
+    def __init__(self, count, boxes, scores, labels):
+        self.count, self.boxes, self.scores, self.labels = count, boxes, scores, labels
+        self.counts = None
+
+    def resolve(self):
+        if self.counts is None:
+            self.counts = [int(c) for c in self.count.cpu().tolist()]     # blocking copy behind the batch's kernels
+        return self.counts
+
+    def frame(self, i):
+        c = self.resolve()[i]
+        return self.boxes[i, :c], {"scores": self.scores[i, :c], "labels": self.labels[i, :c].long()}
 
 
 class _CapturedUnit:

@@ -36,11 +36,14 @@ class BoxList(object):
     # `output = [o.to(cpu_device) for o in output]; results_dict.update(...)` (mega_core/engine/inference.py:75-78) - never
     # blocks on the GPU, and a caller that looks at it immediately gets the same values as before.
     @classmethod
-    def deferred(cls, resolver, image_size, mode="xyxy"):
+    def deferred(cls, resolver, image_size, mode="xyxy", on_host=True):
+        """`on_host`: the resolved tensors live in host memory (then `.to("cpu")` has nothing to do and does not
+        resolve); False for device-resident results whose per-frame detection count is still on the device."""
         self = cls.__new__(cls)
         self._bbox = None
         self._fields = {}
         self._pending = resolver
+        self._pending_on_host = bool(on_host)
         self.size = image_size
         self.mode = mode
         return self
@@ -149,7 +152,7 @@ class BoxList(object):
 
     # ---- container protocol
     def to(self, device):
-        if self._pending is not None and torch.device(device).type == "cpu":
+        if self._pending is not None and getattr(self, "_pending_on_host", True) and torch.device(device).type == "cpu":
             return self          # deferred results land in host memory: nothing to move, nothing to wait for
         out = BoxList(self.bbox.to(device), self.size, self.mode)
         for k, v in self.extra_fields.items():
