@@ -387,7 +387,10 @@ def run_ours(args):
                                                              "52 MB per key batch)" % (args.frames * 7.47)},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": ms_e2e / args.steps,
-                    "input": "fp32 [0,1] ImageLists in pinned host memory (the reference's ToTensor output)"},
+                    "input": "fp32 [0,1] ImageLists in pinned host memory (the reference's ToTensor output)",
+                    "loop": "mega_core/engine/inference.py:66-78 (call, outputs .to(cpu), store); deferred host results "
+                            "(BoxList.deferred) let the host run ahead up to 4 key batches; every detection of the clip "
+                            "is read on the host before the clip's timed region ends"},
             "e2e_u8": {"value": e2e_u8_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_u8,
                        "d2h_bytes_per_step": d2h_u8, "ms_per_step": ms_u8 / args.steps,
                        "input": "uint8 ImageLists in pinned host memory (decoded frames; ToTensor fused into "
