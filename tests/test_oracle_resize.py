@@ -37,3 +37,19 @@ def test_size_rule():
     assert orz.get_size((480, 640)) == (800, 600)
     assert orz.get_size((1000, 600)) == (600, 1000)
     assert orz.get_size((500, 500)) == (600, 600)
+
+
+def test_clip_loader_size_rule_and_argument_checks():
+    """Host side of diffusionvid_b200/clip_loader.py: the size rule equals Resize.get_size (restated in the oracle) on
+    a grid of frame sizes; non-uint8 / non-HWC input is rejected before anything touches the device."""
+    import torch
+    from diffusionvid_b200 import clip_loader
+    for w in (320, 500, 640, 1000, 1280, 1920):
+        for h in (180, 240, 480, 500, 600, 720, 1080):
+            for mn, mx in ((600, 1000), (150, 250), (800, 1333)):
+                assert clip_loader.get_size((w, h), mn, mx) == orz.get_size((w, h), mn, mx)
+    t = clip_loader.GpuFrameTransform(600, 1000, 32, device="cpu")
+    with pytest.raises(ValueError):
+        t(torch.zeros(2, 3, 8, 8, dtype=torch.uint8))            # CHW, not the decoder's HWC
+    with pytest.raises(ValueError):
+        t(torch.zeros(8, 8, 3, dtype=torch.float32))
