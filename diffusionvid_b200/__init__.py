@@ -18,6 +18,11 @@ from .structures import BoxList, ImageList, cat_boxlist, to_image_list  # noqa: 
 
 _DETECTION_META_ARCHITECTURES = {}
 
+# Without a checkout of the reference on the path, `mega_core.structures.bounding_box.BoxList` & co. resolve to this
+# package (diffusionvid_b200/compat.py), so predictions.pth files carry - and load under - the reference's class path.
+from . import compat as _compat  # noqa: E402
+_compat.install_mega_core_alias()
+
 
 def build_detection_model(cfg):
     """Registry lookup by cfg.MODEL.META_ARCHITECTURE, like mega_core.modeling.detector.build_detection_model."""

@@ -91,6 +91,13 @@ def load_state_dict(model, loaded_state_dict):
     """``mega_core.utils.model_serialization.load_state_dict`` for this model.  Returns the untouched model keys."""
     merged, missing = adapt_state_dict(model, loaded_state_dict)
     model.load_state_dict(merged)
+    left = [k for k in missing if k.startswith("head.")]
+    if left:
+        # the model's default initialisation is random (synthetic weights): a head that silently keeps it produces
+        # garbage detections, so say so loudly (the reference only logs "keys are not updated")
+        import warnings
+        warnings.warn("diffusionvid_b200.checkpoint: %d head parameters were not found in the checkpoint and keep "
+                      "their random initialisation, e.g. %s" % (len(left), ", ".join(left[:3])), RuntimeWarning)
     return missing
 
 

@@ -169,6 +169,7 @@ def hot_path_params(cfg):
         all_frame_interval=_get(cfg, "MODEL.VID.MEGA.ALL_FRAME_INTERVAL", 8),
         key_frame_location=_get(cfg, "MODEL.VID.MEGA.KEY_FRAME_LOCATION", 0),
         global_enable=bool(_get(cfg, "MODEL.VID.MEGA.GLOBAL.ENABLE", True)),
+        global_res_stage=int(_get(cfg, "MODEL.VID.MEGA.GLOBAL.RES_STAGE", 1)),
         mem_size=_get(cfg, "MODEL.VID.MEGA.MEMORY_MANAGEMENT_SIZE_TEST", 900),
         mem_size2=150,                      # hard-coded in the reference, diffusion_det.py:487
         topk=(75, 25),                      # hard-coded in the reference, box_head.py:235

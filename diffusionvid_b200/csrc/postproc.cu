@@ -502,7 +502,6 @@ fps_kernel(int n, int m, int log2_bs, const float* __restrict__ dist, float* __r
     float best = -1.f;
     unsigned bprio = 0xFFFFFFFFu;
     const float* row = dist + static_cast<long>(old) * n;
-#pragma unroll
     float rv[FPS_PER_THREAD];
 #pragma unroll
     for (int r = 0; r < FPS_PER_THREAD; ++r) {      // all loads of the round in flight before the first compare

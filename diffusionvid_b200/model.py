@@ -69,6 +69,21 @@ class DiffusionDet(nn.Module):
             raise DvidError("the sm_100a kernels are specialised for HIDDEN_DIM=256, DIM_DYNAMIC=64, NHEADS=8")
         if hp["num_proposals"] > 1024:
             raise DvidError("NUM_PROPOSALS > 1024 is not supported by the per-frame kernels")
+        # limits of the per-frame post-processing kernels (postproc.cu): the NMS candidate list of a frame
+        # ((SAMPLE_STEP-1) * NUM_PROPOSALS ensemble rows) must fit one 1024-slot CTA, and the top-k kernel keeps the
+        # frame's N*C scores plus 1024 (key, index) pairs in shared memory.  Checked here so an unsupported (but legal
+        # in the reference) configuration fails at construction, not inside the first decode / graph capture.
+        cap = max(1, hp["sample_step"] - 1) * hp["num_proposals"]
+        if hp.get("use_nms", True) and cap > 1024:
+            raise DvidError("(SAMPLE_STEP-1)*NUM_PROPOSALS = %d candidates per frame exceeds the 1024 the NMS kernels "
+                            "support" % cap)
+        if 1024 * 8 + hp["num_proposals"] * hp["num_classes"] * 4 > 200 * 1024:
+            raise DvidError("NUM_PROPOSALS*NUM_CLASSES = %d scores per frame exceed the top-k kernel's shared memory"
+                            % (hp["num_proposals"] * hp["num_classes"]))
+        if hp.get("global_enable") and hp.get("num_heads_local", 0) > 0 and int(hp.get("global_res_stage", 1)) != 1:
+            raise DvidError("MODEL.VID.MEGA.GLOBAL.RES_STAGE = %s: only the shipped value 1 (one global attention "
+                            "module, adaptive-norm conditioning, box_head.py:196-211) is implemented"
+                            % hp.get("global_res_stage"))
         self.device = hp["device"]
         self.num_proposals = hp["num_proposals"]
         self.num_classes = hp["num_classes"]
@@ -478,8 +493,11 @@ class DiffusionDet(nn.Module):
             logits, boxes, pro32, pro16 = self._head(e, lv, boxes, pro32, pro16, t)
         return logits, boxes, pro32, pro16
 
-    def _cond_shift(self, e, obj16, M, kv=None):
-        """global cross-attention (box_head.py:366-371) -> SiLU -> c_mlp (box_head.py:644): per-row shift (M,256)."""
+    def _global_context(self, obj16, M, kv=None):
+        """global cross-attention of the base-stage object features over the video memory (box_head.py:366-371),
+        followed by the SiLU that opens every cond head's c_mlp (box_head.py:644): (M,256) fp16.  Computed ONCE per
+        DDIM step - the reference evaluates `attn_` before its cond-head loop and every RCNNHead_cond applies its own
+        c_mlp to that same tensor (box_head.py:366-419)."""
         ga = self._pk["ga"]
         dev = obj16.device
         q = ops.gemm(obj16, ga["q_w"], ga["q_b"])
@@ -489,8 +507,12 @@ class DiffusionDet(nn.Module):
         part, s = ops.gemm_partials(ctx, ga["o_w"], 1)
         cond16 = torch.empty((M, 256), device=dev, dtype=H)
         ops.row_post(M, partials=part, splits=s, bias=ga["o_b"], act2=2, act2_f16_only=True, out_f16=cond16)
+        return cond16
+
+    def _cond_shift(self, e, cond16, M):
+        """c_mlp of cond head `e` on SiLU(attn_) (box_head.py:644): the per-row shift (M,256) fp32."""
         part, s = ops.gemm_partials(cond16, e["cm_w"], 1)
-        shift = torch.empty((M, 256), device=dev, dtype=F32)
+        shift = torch.empty((M, 256), device=cond16.device, dtype=F32)
         ops.row_post(M, partials=part, splits=s, bias=e["cm_b"], out_f32=shift)
         return shift
 
@@ -637,8 +659,9 @@ class DiffusionDet(nn.Module):
                         lg, bx = c_lg[i0:i1], c_bx[i0:i1]
                         o32, o16 = c_o32[i0:i1].reshape(M, 256), c_o16[i0:i1].reshape(M, 256)
                     if use_cond:
+                        cond16 = self._global_context(o16.contiguous(), M, mem_kv)
                         for e in pk["cond"]:
-                            shift = self._cond_shift(e, o16.contiguous(), M, mem_kv)
+                            shift = self._cond_shift(e, cond16, M)
                             lg, bx, o32, o16 = self._head(e, lv, bx.contiguous(), o32.contiguous(), o16.contiguous(),
                                                           t, shift_rows=shift)
                     logits, coord = lg.contiguous(), bx.contiguous()

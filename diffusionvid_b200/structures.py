@@ -7,10 +7,36 @@ VID evaluator keep working unchanged:
   cat_boxlist - mega_core/structures/boxlist_ops.py:103-133
 
 Only the members the DiffusionVID inference path and its callers touch are provided.
+
+Pickle contract (SURVEY.md 8b "output artefact"): `predictions.pth` is `torch.save(list[BoxList])` and its consumers
+(`tools/test_prediction.py`, `vid_eval.py:14-25`) unpickle `mega_core.structures.bounding_box.BoxList`.  BoxLists made
+here therefore pickle under THAT class path (`BoxList.__reduce_ex__`): when the reference's package is importable its own
+class is named in the stream (the reference's class has no `__setstate__`, so the state dict - bbox / size / mode /
+extra_fields - lands in its `__dict__`), otherwise `diffusionvid_b200.compat` registers alias modules under the
+`mega_core.*` names that resolve to the classes of this file.
 """
+import copyreg
+import importlib
 import math
+import sys
 
 import torch
+
+_REF_BOXLIST_MODULE = "mega_core.structures.bounding_box"
+
+
+def _pickle_class():
+    """The class object that pickled BoxLists name: `mega_core.structures.bounding_box.BoxList` (the reference's own
+    class when that package is importable, else this package's alias of it), falling back to this module's class."""
+    mod = sys.modules.get(_REF_BOXLIST_MODULE)
+    if mod is None:
+        try:
+            mod = importlib.import_module(_REF_BOXLIST_MODULE)
+        except Exception:
+            from . import compat
+            mod = compat.install_mega_core_alias().get(_REF_BOXLIST_MODULE)
+    cls = getattr(mod, "BoxList", None) if mod is not None else None
+    return cls if isinstance(cls, type) else BoxList
 
 
 class BoxList(object):
@@ -78,6 +104,12 @@ class BoxList(object):
     def __getstate__(self):      # pickled like the reference's BoxList: bbox / size / mode / extra_fields
         self._materialize()
         return {"bbox": self._bbox, "size": self.size, "mode": self.mode, "extra_fields": self._fields}
+
+    def __reduce_ex__(self, protocol):
+        # class reference = mega_core.structures.bounding_box.BoxList (see the module docstring), state = its attributes
+        # (copyreg._reconstructor is what protocol < 2 pickles of plain objects use; unlike __newobj__ it may name a class
+        # other than type(self))
+        return copyreg._reconstructor, (_pickle_class(), object, None), self.__getstate__()
 
     def __setstate__(self, state):
         self._bbox = state["bbox"]
@@ -209,7 +241,9 @@ class ImageList(object):
 def to_image_list(tensors, size_divisible=0):
     if isinstance(tensors, torch.Tensor) and size_divisible > 0:
         tensors = [tensors]
-    if isinstance(tensors, ImageList):
+    if isinstance(tensors, ImageList) or (hasattr(tensors, "tensors") and hasattr(tensors, "image_sizes")):
+        # any ImageList look-alike passes through untouched - in particular the reference's own class
+        # (mega_core/structures/image_list.py:7-27), which is what engine/inference.py:35-40 hands to the model
         return tensors
     if isinstance(tensors, torch.Tensor):
         if tensors.dim() == 3:

@@ -28,6 +28,17 @@ def match_fraction(got_boxes, got_scores, got_labels, ref_boxes, ref_scores, ref
     return hit / n
 
 
+def match_fraction_two_sided(got_boxes, got_scores, got_labels, ref_boxes, ref_scores, ref_labels, img_max,
+                             box_tol=1e-3, score_tol=2e-3):
+    """min(reference -> product, product -> reference): spurious extra detections (NMS under-suppression, stale rows
+    past `count`) lower the score just like missing ones do."""
+    fwd = match_fraction(got_boxes, got_scores, got_labels, ref_boxes, ref_scores, ref_labels, img_max, box_tol,
+                         score_tol)
+    bwd = match_fraction(ref_boxes, ref_scores, ref_labels, got_boxes, got_scores, got_labels, img_max, box_tol,
+                         score_tol)
+    return min(fwd, bwd)
+
+
 def rows_within(a, b, tol):
     """fraction of rows of a/b (.., D) whose max-abs difference is <= tol."""
     d = (a - b).abs().reshape(-1, a.shape[-1]).max(dim=1)[0]

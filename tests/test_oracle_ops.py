@@ -131,3 +131,22 @@ def test_apply_deltas_identity_and_clamp():
     assert torch.allclose(out, boxes)
     big = om.apply_deltas(torch.tensor([[0., 0., 50., 50.]]), boxes)
     assert abs((big[0, 2] - big[0, 0]).item() - 100.0 * 100000.0 / 16) / (100.0 * 100000.0 / 16) < 1e-5
+
+
+def test_cdist_direct_vs_the_reference_call_and_fps_picks():
+    """The reference calls torch.cdist(feats, feats, p=2.0) with the DEFAULT compute mode (diffusion_det.py:880), which
+    for n > 25 takes the matmul route (|a|^2 + |b|^2 - 2ab, clamp, sqrt); the oracle and the sm_100a kernel take direct
+    differences (oracle/ops.py::cdist_l2).  The two differ by fp32 cancellation error only.  Bound it on memory-like
+    rows (LayerNorm outputs, 256 wide, as update_erase_memory sees them: 600 -> 150 and 1800 -> 900), and check that
+    farthest-point sampling picks the same rows from either matrix up to near-tie swaps."""
+    for seed, (n, m) in enumerate([(600, 150), (1800, 900)]):
+        x = torch.nn.functional.layer_norm(torch.randn(n, 256, generator=gen(40 + seed)) * 1.5, (256,))
+        direct = oo.cdist_l2(x)
+        ref = torch.cdist(x, x, p=2.0)                       # 'use_mm_for_euclid_dist_if_necessary' -> mm path here
+        off = ~torch.eye(n, dtype=torch.bool)
+        rel = ((direct - ref).abs()[off] / ref[off]).max().item()
+        assert rel <= 2e-5, rel                              # fp32 cancellation of the mm route at |x|^2 = 256
+        assert direct.diagonal().abs().max().item() == 0.0   # exact zeros on the diagonal (the mm route leaves ~1e-3)
+        a = set(oo.fps(direct.numpy(), m).tolist())
+        b = set(oo.fps(ref.numpy(), m).tolist())
+        assert len(a & b) >= 0.97 * m, (len(a & b), m)
