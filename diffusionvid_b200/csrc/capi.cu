@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 9
+#define DVID_ABI_VERSION 10
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -40,6 +40,14 @@ int dvid_gemm_f16(const void* a, const void* w, const float* bias, const void* r
   if (splits_used) *splits_used = used;
   return dvid::conv_gemm_launch(a, w, bias, resid, out_f32_partials ? nullptr : out_f16, out_f32_partials, 1, 1, m, k,
                                 n, 1, 1, 1, 0, 0, relu, splits, 0, S(stream));
+}
+
+int dvid_roi_align_legacy_forward(const float* input, const float* rois, int num_rois, int channels, int height,
+                                  int width, float spatial_scale, int pooled_height, int pooled_width,
+                                  int sampling_ratio, float* out, void* stream) {
+  if (num_rois > 0 && (!input || !rois || !out)) return DVID_ERR_ARG;
+  return dvid::roi_align_legacy_launch(input, rois, num_rois, channels, height, width, spatial_scale, pooled_height,
+                                       pooled_width, sampling_ratio, out, S(stream));
 }
 
 int dvid_conv_streamk(int enable) { return dvid::conv_streamk_enable(enable); }

@@ -74,6 +74,9 @@ int nms_launch(const float* boxes, const float* scores, const int* labels, const
 int cdist_launch(const float* x, float* out, int n, int d, cudaStream_t stream);
 int fps_launch(int b, int n, int m, const float* dist, float* temp, int* idx, cudaStream_t stream);
 
+int roi_align_legacy_launch(const float* in, const float* rois, int num_rois, int C, int H, int W, float scale, int PH,
+                            int PW, int sampling_ratio, float* out, cudaStream_t stream);
+
 int head_tail_launch(const void* fc, const void* cls_w, const float* cls_g, const float* cls_b, const void* logit_w,
                      const float* logit_bias, int C, const void* const* reg_w, const float* const* reg_g,
                      const float* const* reg_b, const void* delta_w, const float* delta_bias, const float* boxes_in,

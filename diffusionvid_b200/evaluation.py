@@ -15,7 +15,13 @@ Conventions kept from the reference because they change numbers:
   * classes that occur only in predictions have no recall -> AP = nan and are skipped by the mean (:281-289, :160).
   * CorLoc looks at the single top-scoring detection of an image and counts once per ground-truth BOX of a class
     (:377-417), not once per image.
-Motion-specific AP (`motion_specific=True`, needs the dataset's motion-IoU .mat file) is not implemented.
+Motion-specific AP (`motion_specific=True`, vid_eval.py:39-44,142-149,172-181,192-197,233-264,279-283): every ground
+truth box carries a "motion IoU" (how much it moves over +-10 frames; shipped with the dataset as
+vid_groundtruth_motion_iou.mat); for a range [lo, hi] the boxes outside it are *ignored*: they do not count as
+positives, a detection matched to one is neither true nor false positive, an unmatched detection is dropped when its
+best overlap is with an ignored box, counted fully when it is with a regular one and with the image's ignored fraction
+on a tie, and detections on images without ground truth of their class weigh `empty_weight` = the share of all boxes
+inside the range.  `load_motion_ious` reads the .mat file the way the reference does.
 """
 import os
 
@@ -44,54 +50,102 @@ def _fields(bl, device):
             bl.get_field("scores").to(device, F32).reshape(-1) if bl.has_field("scores") else None)
 
 
-def match_detections(pred_boxlists, gt_boxlists, iou_thresh=0.5, device="cpu"):
-    """Greedy VID matching.  Returns (scores, labels, hits) of all detections concatenated in image order (within an
-    image: descending score) and the number of ground-truth boxes per class (dict)."""
+def load_motion_ious(mat_file):
+    """vid_eval.py:142-147: the dataset's per-image lists of ground-truth motion IoUs (empty entries -> 0)."""
+    import scipy.io as sio
+    m = sio.loadmat(mat_file)["motion_iou"]
+    return [[(m[i][0][j][0] if len(m[i][0][j]) != 0 else 0) for j in range(len(m[i][0]))] for i in range(len(m))]
+
+
+def match_detections(pred_boxlists, gt_boxlists, iou_thresh=0.5, device="cpu", motion_ious=None,
+                     motion_range=(0.0, 1.0)):
+    """Greedy VID matching.  Returns (scores, labels, hits, ignore) of all detections concatenated in image order
+    (within an image: descending score) and the number of countable ground-truth boxes per class (dict).
+    `ignore` is the reference's `pred_ignore` (vid_eval.py:170,221,254-263): 0 = regular, 1 = dropped, in between =
+    fractional false-positive weight; all zeros without `motion_ious`."""
     if len(pred_boxlists) != len(gt_boxlists):
         raise ValueError("Length of gt and pred lists need to be same.")
-    scores, labels, hits = [], [], []
+    lo, hi = motion_range
+    if motion_ious is None:
+        motion_ious = [None] * len(gt_boxlists)
+        empty_weight = 0.0
+    else:
+        allm = np.concatenate([np.asarray(m, dtype=np.float64).reshape(-1) for m in motion_ious], axis=0)
+        empty_weight = float(((allm >= lo) & (allm <= hi)).sum()) / float(len(allm))
+        if empty_weight == 1:
+            empty_weight = 0.0
+    scores, labels, hits, ignores = [], [], [], []
     n_pos = {}
-    for pred, gt in zip(pred_boxlists, gt_boxlists):
+    for pred, gt, miou in zip(pred_boxlists, gt_boxlists, motion_ious):
         pb, pl, ps = _fields(pred, device)
         gb, gl, _ = _fields(gt, device)
-        for l, c in zip(*[t.tolist() for t in torch.unique(gl, return_counts=True)]):
-            n_pos[l] = n_pos.get(l, 0) + c
+        ign = torch.zeros(gb.shape[0], dtype=torch.bool)
+        if miou is not None and len(miou):                     # `if motion_iou:` on the per-image list (:192)
+            mi = torch.as_tensor(np.asarray(miou, dtype=np.float64))
+            ign = (mi < lo) | (mi > hi)
+        glc = gl.cpu()
+        for l in torch.unique(glc).tolist():
+            own = glc == l
+            n_pos[l] = n_pos.get(l, 0) + int(own.sum()) - int((own & ign).sum())
         for l in torch.unique(pl).tolist():
             n_pos.setdefault(l, 0)
         if pb.shape[0] == 0:
             continue
         order = torch.sort(ps, descending=True, stable=True)[1]
         pb, pl, ps = pb[order], pl[order], ps[order]
-        hit = torch.zeros(pb.shape[0], dtype=torch.bool, device=pb.device)
+        hit = torch.zeros(pb.shape[0], dtype=torch.bool)
+        pig = torch.zeros(pb.shape[0], dtype=torch.float64)
+        plc = pl.cpu()
         if gb.shape[0] > 0:
             iou = _vid_iou(pb, gb)
-            iou = torch.where(pl[:, None] == gl[None, :], iou, torch.full_like(iou, -1.0))   # own class only
-            iou = iou.cpu()
+            iou = torch.where(pl[:, None] == gl[None, :], iou, torch.full_like(iou, -1.0)).cpu()   # own class only
             free = torch.ones(gb.shape[0], dtype=torch.bool)
-            for j in range(iou.shape[0]):
-                cand = torch.where(free & (iou[j] >= iou_thresh), iou[j], torch.full_like(iou[j], -1.0))
-                k = int(torch.argmax(cand))                  # first maximum, like the reference's scan
-                if cand[k] >= iou_thresh:
-                    free[k] = False
-                    hit[j] = True
-        scores.append(ps.cpu()); labels.append(pl.cpu()); hits.append(hit.cpu())
+        for j in range(pb.shape[0]):
+            own = glc == plc[j] if gb.shape[0] > 0 else torch.zeros(0, dtype=torch.bool)
+            n_own = int(own.sum())
+            if n_own == 0:                                       # no ground truth of this class in the image (:219-222)
+                pig[j] = empty_weight
+                continue
+            row = iou[j]
+            cand = free & own & (row >= iou_thresh)
+            if bool(cand.any()):
+                best = row[cand].max()
+                ties = torch.nonzero(cand & (row == best)).flatten().tolist()
+                # the reference's ascending scan (:236-252): a later tie replaces the current pick while that is ignored
+                k = ties[0]
+                for t in ties[1:]:
+                    if bool(ign[k]):
+                        k = t
+                free[k] = False
+                hit[j] = True
+                pig[j] = float(ign[k])
+            else:                                                # unmatched (:258-264)
+                ig = row[own & ign].max().item() if bool((own & ign).any()) else -1.0
+                nig = row[own & ~ign].max().item() if bool((own & ~ign).any()) else -1.0
+                pig[j] = 0.0 if nig > ig else (1.0 if ig > nig else float((own & ign).sum()) / float(n_own))
+        scores.append(ps.cpu()); labels.append(plc); hits.append(hit); ignores.append(pig)
     cat = lambda xs, dt: torch.cat(xs) if xs else torch.zeros(0, dtype=dt)
-    return cat(scores, F32), cat(labels, torch.int64), cat(hits, torch.bool), n_pos
+    return (cat(scores, F32), cat(labels, torch.int64), cat(hits, torch.bool), cat(ignores, torch.float64)), n_pos
 
 
-def precision_recall(scores, labels, hits, n_pos):
-    """Per-class precision / recall arrays (index = class id; None where the class never occurs / has no ground
-    truth), vid_eval.py:265-291 with no ignored boxes."""
+def precision_recall(records, n_pos):
+    """Per-class precision / recall arrays (index = class id; None where the class never occurs / has no countable
+    ground truth), vid_eval.py:265-291."""
+    scores, labels, hits, ignores = records
     n_cls = (max(n_pos) + 1) if n_pos else 0
     prec, rec = [None] * n_cls, [None] * n_cls
     scores, hits = scores.numpy().astype(np.float64), hits.numpy()
-    labels = labels.numpy()
+    labels, ignores = labels.numpy(), ignores.numpy()
     for l in n_pos:
         sel = labels == l
         order = np.argsort(-scores[sel], kind="stable")
         h = hits[sel][order]
-        tp = np.cumsum(h)
-        fp = np.cumsum(~h)
+        w = ignores[sel][order].copy()
+        tps = np.logical_and(h, w != 1)
+        fps = np.logical_and(~h, w != 1)
+        w[w == 0] = 1
+        tp = np.cumsum(tps)
+        fp = np.cumsum(fps * w)
         prec[l] = tp / (fp + tp + np.spacing(1))
         if n_pos[l] > 0:
             rec[l] = tp / n_pos[l]
@@ -116,11 +170,24 @@ def average_precision(prec, rec, use_07_metric=False):
     return ap
 
 
-def eval_detection_vid(pred_boxlists, gt_boxlists, iou_thresh=0.5, use_07_metric=False, device="cpu"):
-    """-> {"ap": per-class AP array (nan where undefined, index 0 = background), "map": nanmean}."""
-    prec, rec = precision_recall(*match_detections(pred_boxlists, gt_boxlists, iou_thresh, device))
+MOTION_RANGES = (("all", (0.0, 1.0)), ("fast", (0.0, 0.7)), ("medium", (0.7, 0.9)), ("slow", (0.9, 1.0)))   # :40-41
+
+
+def eval_detection_vid(pred_boxlists, gt_boxlists, iou_thresh=0.5, use_07_metric=False, device="cpu",
+                       motion_ious=None, motion_range=(0.0, 1.0)):
+    """-> {"ap": per-class AP array (nan where undefined, index 0 = background), "map": nanmean}.  With `motion_ious`
+    (per image: one value per ground-truth box) the boxes outside `motion_range` are ignored (motion-specific AP)."""
+    prec, rec = precision_recall(*match_detections(pred_boxlists, gt_boxlists, iou_thresh, device, motion_ious,
+                                                   motion_range))
     ap = average_precision(prec, rec, use_07_metric)
     return {"ap": ap, "map": float(np.nanmean(ap)) if len(ap) else float("nan")}
+
+
+def eval_detection_vid_motion(pred_boxlists, gt_boxlists, motion_ious, iou_thresh=0.5, use_07_metric=False,
+                              device="cpu"):
+    """vid_eval.py:39-51 with motion_specific=True: {"all" | "fast" | "medium" | "slow": {"ap", "map"}}."""
+    return {name: eval_detection_vid(pred_boxlists, gt_boxlists, iou_thresh, use_07_metric, device, motion_ious, rng)
+            for name, rng in MOTION_RANGES}
 
 
 def corloc_eval_detection_vid(pred_boxlists, gt_boxlists, iou_thresh=0.5, device="cpu"):
@@ -142,19 +209,28 @@ def corloc_eval_detection_vid(pred_boxlists, gt_boxlists, iou_thresh=0.5, device
     return corloc, (sum(corloc.values()) / len(corloc) if corloc else float("nan"))
 
 
-def do_vid_evaluation(dataset, predictions, output_folder=None, logger=None, device="cpu"):
-    """vid_eval.py:14-81 for the branch the DiffusionVID configs take (box_only=False, motion_specific=False):
-    predictions are resized to the original image size, AP50 per class + mAP + CorLoc are logged and written to
-    `result.txt`.  `dataset` provides get_img_info(i) -> {"width","height"}, get_groundtruth(i) -> BoxList and
-    map_class_id_to_class_name(i)."""
+def do_vid_evaluation(dataset, predictions, output_folder=None, logger=None, device="cpu", motion_ious=None):
+    """vid_eval.py:14-81 (box_only=False): predictions are resized to the original image size, AP50 per class + mAP +
+    CorLoc are logged and written to `result.txt`.  `motion_ious` (list per image, or the path of the dataset's
+    vid_groundtruth_motion_iou.mat) switches on the motion-specific report (`motion_specific=True`: one AP50 line each
+    for all / fast / medium / slow).  `dataset` provides get_img_info(i) -> {"width","height"}, get_groundtruth(i) ->
+    BoxList and map_class_id_to_class_name(i)."""
     preds, gts = [], []
     for i, p in enumerate(predictions):
         info = dataset.get_img_info(i)
         preds.append(p.resize((info["width"], info["height"])))
         gts.append(dataset.get_groundtruth(i))
-    res = eval_detection_vid(preds, gts, 0.5, False, device)
+    if isinstance(motion_ious, (str, bytes)):
+        motion_ious = load_motion_ious(motion_ious)
+    if motion_ious is not None:
+        by_motion = eval_detection_vid_motion(preds, gts, motion_ious, 0.5, False, device)
+        res = by_motion["all"]
+    else:
+        res = eval_detection_vid(preds, gts, 0.5, False, device)
+        by_motion = {"all": res}
     corloc, corloc_avg = corloc_eval_detection_vid(preds, gts, 0.5, device)
-    s = "AP50 | motion={:>6s} = {:0.4f}\n".format("all", res["map"]) + "Category AP:\n"
+    s = "".join("AP50 | motion={:>6s} = {:0.4f}\n".format(name, r["map"]) for name, r in by_motion.items())
+    s += "Category AP:\n"
     for i, ap in enumerate(res["ap"]):
         if i > 0:
             s += "{:<16}: {:.4f}\n".format(dataset.map_class_id_to_class_name(i), ap)
@@ -166,4 +242,4 @@ def do_vid_evaluation(dataset, predictions, output_folder=None, logger=None, dev
     if output_folder:
         with open(os.path.join(output_folder, "result.txt"), "w") as f:
             f.write(s)
-    return dict(res, corloc=corloc, corloc_avg=corloc_avg, text=s)
+    return dict(res, corloc=corloc, corloc_avg=corloc_avg, text=s, motion={k: v["map"] for k, v in by_motion.items()})

@@ -459,3 +459,19 @@ def furthest_point_sampling(b, n, m, dist, temp, idx):
           "dvid_furthest_point_sampling")
     _cnt()
     return 1
+
+
+def roi_align_legacy_forward(inp, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio):
+    """mega_core._C.roi_align_forward (csrc/ROIAlign.h:11-27): input (N,C,H,W) fp32, rois (n,5) fp32 ->
+    (n,C,ph,pw) fp32, maskrcnn-benchmark semantics (no half-pixel shift, roi size >= 1)."""
+    _chk(inp, F32, "input"); _chk(rois, F32, "rois")
+    if inp.dim() != 4 or rois.dim() != 2 or rois.shape[1] != 5:
+        raise DvidError("roi_align_forward: input (N,C,H,W), rois (n,5)")
+    n = rois.shape[0]
+    N, C, Hh, Ww = inp.shape
+    out = torch.empty((n, C, int(pooled_height), int(pooled_width)), device=inp.device, dtype=F32)
+    check(_lib.lib().dvid_roi_align_legacy_forward(ptr(inp), ptr(rois), n, C, Hh, Ww, float(spatial_scale),
+                                                   int(pooled_height), int(pooled_width), int(sampling_ratio),
+                                                   ptr(out), cur_stream()), "dvid_roi_align_legacy_forward")
+    _cnt()
+    return out

@@ -195,6 +195,16 @@ DVID_API int dvid_cdist_f32(const float* x, float* out, int n, int d, void* stre
 DVID_API int dvid_furthest_point_sampling(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Legacy operators of mega_core._C outside the DiffusionVID path, csrc/legacy_ops.cu.
+ */
+/* Drop-in for mega_core._C.roi_align_forward (mega_core/csrc/ROIAlign.h:11-27, cuda/ROIAlign_cuda.cu:65-125,256-300):
+ * the maskrcnn-benchmark ROIAlign - NO half-pixel shift, roi size clamped to >= 1, sampling_ratio <= 0 = adaptive grid.
+ * input [N][C][H][W] fp32, rois [num_rois][5] fp32 = (batch index, x1, y1, x2, y2), out [num_rois][C][ph][pw] fp32. */
+DVID_API int dvid_roi_align_legacy_forward(const float* input, const float* rois, int num_rois, int channels,
+                                           int height, int width, float spatial_scale, int pooled_height,
+                                           int pooled_width, int sampling_ratio, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Swin Transformer backbone (mega_core/modeling/backbone/swintransformer.py), csrc/swin.cu.  The linear layers
  * (qkv / proj / fc1+GELU / fc2 / reduction / patch-embed projection) are dvid_gemm_f16 calls.
  */

@@ -107,3 +107,47 @@ def test_do_vid_evaluation_writes_result_file(tmp_path):
     assert abs(out["map"] - sc["map"]) <= 1e-12
     text = open(os.path.join(str(tmp_path), "result.txt")).read()
     assert text.startswith("AP50 | motion=   all = %.4f" % sc["map"]) and "Mean CorLoc: %.4f" % sc["corloc_avg"] in text
+
+
+def _motion_scenarios():
+    with open(os.path.join(HERE, "golden", "vid_eval_motion_vectors.json")) as f:
+        return json.load(f)["scenarios"]
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_motion_specific_ap_matches_the_reference_evaluator(idx):
+    """vid_eval.py:39-44 (motion_specific=True): all / fast / medium / slow AP50 with ignored ground truth, golden
+    vectors from the reference's own calc_detection_vid_prec_rec (tests/golden/make_golden_eval_motion.py)."""
+    sc = _motion_scenarios()[idx]
+    preds, gts = _boxlists(sc["images"])
+    motion = [im["motion_iou"] for im in sc["images"]]
+    res = ev.eval_detection_vid_motion(preds, gts, motion)
+    assert list(res) == ["all", "fast", "medium", "slow"]
+    for name, want in sc["motion"].items():
+        got = res[name]
+        assert len(got["ap"]) == len(want["ap"])
+        for a, w in zip(got["ap"], want["ap"]):
+            if w is None:
+                assert math.isnan(a)
+            else:
+                assert abs(a - w) <= 1e-12, (name, a, w)
+        assert abs(got["map"] - want["map"]) <= 1e-12
+
+
+def test_motion_report_lines(tmp_path):
+    sc = _motion_scenarios()[0]
+    preds, gts = _boxlists(sc["images"])
+
+    class DS:
+        def get_img_info(self, i):
+            return {"width": sc["images"][i]["size"][0], "height": sc["images"][i]["size"][1]}
+
+        def get_groundtruth(self, i):
+            return gts[i]
+
+        def map_class_id_to_class_name(self, i):
+            return "class%d" % i
+    out = ev.do_vid_evaluation(DS(), preds, str(tmp_path), motion_ious=[im["motion_iou"] for im in sc["images"]])
+    lines = out["text"].splitlines()
+    for i, name in enumerate(("all", "fast", "medium", "slow")):
+        assert lines[i] == "AP50 | motion={:>6s} = {:0.4f}".format(name, sc["motion"][name]["map"])

@@ -150,3 +150,17 @@ def test_cdist_direct_vs_the_reference_call_and_fps_picks():
         a = set(oo.fps(direct.numpy(), m).tolist())
         b = set(oo.fps(ref.numpy(), m).tolist())
         assert len(a & b) >= 0.97 * m, (len(a & b), m)
+
+
+@pytest.mark.parametrize("sampling_ratio", [2, 0])
+def test_legacy_roi_align_restatement_matches_torchvision(sampling_ratio):
+    """oracle/legacy.py::roi_align_legacy (csrc/cuda/ROIAlign_cuda.cu:65-125) against the installed torchvision
+    roi_align(aligned=False): same algorithm (both derive from caffe2's), incl. malformed / out-of-image rois."""
+    from oracle import legacy
+    g = gen(77)
+    feat = torch.randn(2, 5, 20, 30, generator=g)
+    rois = torch.tensor([[0, 10., 12., 100., 90.], [1, -20., -8., 40., 33.], [0, 50., 50., 50., 50.],
+                         [1, 200., 100., 260., 170.], [0, 0., 0., 239., 159.], [1, 30.5, 20.25, 28., 19.]])
+    got = legacy.roi_align_legacy(feat.numpy(), rois.numpy(), 0.125, 7, 7, sampling_ratio)
+    ref = torchvision.ops.roi_align(feat, rois, (7, 7), 0.125, sampling_ratio, False)
+    assert np.abs(got - ref.numpy()).max() <= 2e-6
