@@ -80,7 +80,7 @@ def swin_block(c, pre, x, H, W, heads, ws, shift, mask):
     q, k, v = qkv[0] * (hd ** -0.5), qkv[1], qkv[2]
     attn = q @ k.transpose(-2, -1)
     table = sd[pre + "attn.relative_position_bias_table"]
-    bias = table[relative_position_index(ws).view(-1)].view(N, N, -1).permute(2, 0, 1).contiguous()
+    bias = table[relative_position_index(ws).view(-1).to(table.device)].view(N, N, -1).permute(2, 0, 1).contiguous()
     attn = attn + bias.unsqueeze(0)
     if shift > 0:
         nW = mask.shape[0]
@@ -144,7 +144,7 @@ def swin_body(c, x, out_indices=(1, 2, 3), p="backbone.bottom_up."):
     x = _ln(x, sd, p + "patch_embed.norm")
     outs = {}
     for i, (depth, nh) in enumerate(zip(depths, heads)):
-        mask = shift_mask(Wh, Ww, ws, ws // 2)
+        mask = shift_mask(Wh, Ww, ws, ws // 2).to(x.device)
         for b in range(depth):
             x = swin_block(c, "%slayers.%d.blocks.%d." % (p, i, b), x, Wh, Ww, nh, ws, 0 if b % 2 == 0 else ws // 2,
                            mask)
