@@ -18,11 +18,20 @@ reference frames at the video start (backbone + 3 base stages on all 88 frames, 
           the reference's ToTensor is evaluated by the first GPU kernel, a quarter of the bytes cross PCIe.
   roofline : the dominant kernel family (tcgen05 conv/GEMM), algorithmic FLOPs / CUDA-event time measured live in a
           separate instrumented pass, against MEASURED_PEAKS.json (bf16 dense, sustained).
+  e2e_engine : the e2e clip driven EXACTLY like mega_core/engine/inference.py:26-93 with its timer on: every call first
+          moves `cur` and every ref ImageList to the device (:35-40; `cur` is a second upload of a frame that also
+          arrives as a ref), the model is called, torch.cuda.synchronize() (:70-73), outputs .to(cpu) (:75).
   cpu_baseline / --impl reference : the fp32 CPU oracle (oracle/model.py, a PyTorch restatement of the reference; the
-          reference itself cannot be imported - SURVEY.md 8c) on the host cores, on a bounded sample of the workload.
+          reference itself cannot be imported - SURVEY.md 8c) on the host cores, on a bounded sample of the workload:
+          one key batch of 8 frames + 13 global frames (975 -> 900 farthest-point sampling active), N=300, T=4.
+  parity : the product against the oracle ON THE SAME SAMPLE inside the cpu_baseline leg: detections of that clip
+          (two-sided matched fraction), and on two frames the per-head box / logit deltas on identical inputs against
+          the fp16-emulating oracle + index-exact top-k/NMS on identical inputs.
 
 N>1 (torchrun): video-level sharding as in the reference (VIDTestDistributedSampler): every rank processes its own
-clips, no data-path collective; value = total frames of all ranks / max-over-ranks time ("weak" scaling).
+clips, no data-path collective; value = total frames of all ranks / max-over-ranks time ("weak" scaling).  The line
+additionally carries `frame_sharded`: ONE clip dealt frame by frame to the N ranks (BASELINE config 5; strong scaling,
+one all-gather of memory candidates per video + one all-gather of detections per key batch).
 """
 import argparse
 import json
@@ -54,7 +63,10 @@ def parse():
     ap.add_argument("--width", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--cpu-sample-frames", type=int, default=8, help="key-batch frames of the CPU oracle sample")
+    ap.add_argument("--cpu-sample-global", type=int, default=13, help="global frames of the CPU oracle sample")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-frame-sharded", action="store_true", help="N>1: skip the frame-sharded sub-measurement")
     ap.add_argument("--backbone", default="r101", choices=["r101", "swinb"],
                     help="r101: vid_R_101_DiffusionVID.yaml (headline); swinb: vid_Swin_B_DiffusionVID.yaml "
                          "(INFER_BATCH 4, ALL_FRAME_INTERVAL 4)")
@@ -90,23 +102,149 @@ def cpu_oracle_run(args, frames_n, global_n, repeats):
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.make_state_dict(seed=1234, blocks=HP_BASE["blocks"])
     ocfg = dict(num_proposals=args.proposals, sample_step=args.T)
-    frames = synth.make_clip(frames_n, args.height, args.width, seed=1234)
-    gidx = [min(frames_n - 1, (i * 7) % frames_n) for i in range(global_n)]
-    samples = synth.clip_samples(frames, gidx, args.height, args.width)
+    frames = synth.make_clip(frames_n + global_n, args.height, args.width, seed=1234)
+    samples = synth.clip_samples(frames[:frames_n], [], args.height, args.width)
+    samples[0]["ref_g"] = [frames[frames_n + i][None] for i in range(global_n)]      # global frames: distinct images
     times = []
+    last = None
     for r in range(repeats):
-        o = om.OracleDiffusionVID(sd, ocfg, fp16=False, noise=om.NoiseSource(1234 + r, args.proposals))
+        o = om.OracleDiffusionVID(sd, ocfg, fp16=False, noise=om.NoiseSource(1234, args.proposals))
         t0 = time.perf_counter()
-        n_out = 0
+        res = []
         with torch.no_grad():
             for s in samples:
-                n_out += len(o.forward(s))
+                res += o.forward(s)
         times.append(time.perf_counter() - t0)
-        assert n_out == frames_n
-    best = min(times)
+        assert len(res) == frames_n
+        last = (o, res)
+    best = min(times) if times else float("nan")
     desc = ("%d-frame clip + %d global frames, N=%d, T=%d, %dx%d, R-101+FPN, fp32 PyTorch oracle, %d threads"
             % (frames_n, global_n, args.proposals, args.T, args.width, args.height, torch.get_num_threads()))
-    return frames_n / best, desc, times
+    return frames_n / best, desc, times, (sd, samples, last)
+
+
+def cpu_sample_for_budget(args, steps, budget_s=240.0):
+    """--impl reference runs the sample (steps + 1 warm-up) times: pick the largest sample clip whose run still ends
+    within a few minutes.  Costs are the measured 16-thread times of the fp32 oracle per sample (profiles/README.md);
+    they only steer the choice, the line reports what was actually run."""
+    est = [((8, 13), 45.0), ((8, 4), 28.0), ((4, 2), 14.0), ((2, 1), 6.0)]
+    want = (args.cpu_sample_frames, args.cpu_sample_global)
+    for (f, g), cost in est:
+        if f <= want[0] and g <= want[1] and cost * (steps + 1) <= budget_s:
+            return f, g
+    return 2, 1
+
+
+# ---------------------------------------------------------------------------------------------------- parity (cpu leg)
+def parity_report(args, dev, pack):
+    """The product against the oracle on the cpu_baseline sample (part of the cpu_baseline leg: the oracle is used
+    here as the CHECKER of the product's outputs, never on the measured path).
+      match        two-sided matched fraction of the final detections of the sample's key batch vs the fp32 oracle run
+                   that was just timed (box 2e-3 of the image size, score 4e-3); for T > 1 one differing renewal decision
+                   re-deals a whole frame's step noise, so the number of such flips is reported next to it
+      box_delta /  per-head differences on IDENTICAL inputs (teacher forced) against the fp16-emulating oracle, two
+      logit_delta  frames, three base heads + the conditioned head on the oracle's own 900-row memory
+      keep_equal   top-k as a set and NMS keep order index-exact when fed the oracle's logits / candidate lists"""
+    from diffusionvid_b200 import model as pm, ops, structures
+    from oracle import model as om, ops as oo
+    from tests.parity_util import match_fraction_two_sided, quantiles
+    sd, samples, (o32, ref) = pack
+    h, w, N, T = args.height, args.width, args.proposals, args.T
+    size = float(max(h, w))
+    hp = dict(HP_BASE, num_proposals=N, sample_step=T, device=str(dev))
+    m = pm.DiffusionDet(hp)
+    m.load_state_dict(sd, strict=False)
+    m.to(dev)
+    m.noise = om.NoiseSource(1234, N)
+    m.debug_trace = True
+    L = len(samples)
+    got = []
+    for s in samples:
+        got += m(dict(cur=structures.ImageList(s["cur"].to(dev), [(h, w)]),
+                      ref_l=[structures.ImageList(t.to(dev), [(h, w)]) for t in s["ref_l"]],
+                      ref_g=[structures.ImageList(t.to(dev), [(h, w)]) for t in s["ref_g"]],
+                      frame_id=s["frame_id"], start_id=0, end_id=L - 1, seg_len=L,
+                      frame_category=s["frame_category"], video_id=0))
+    fr = [match_fraction_two_sided(g.bbox.cpu(), g.get_field("scores").cpu(), g.get_field("labels").cpu(),
+                                   r["boxes"], r["scores"], r["labels"], size, box_tol=2e-3, score_tol=4e-3)
+          for g, r in zip(got, ref)]
+    flips = 0
+    for si in range(max(0, T - 1)):
+        kp = torch.sigmoid(m.last_trace[("logits", 0, si, 0)]).max(-1)[0].cpu() > 0.5
+        ko = torch.sigmoid(o32.trace[("logits", 0, si)]).max(-1)[0] > 0.5
+        flips += int((kp != ko).sum())
+    out = {"checker": "oracle/model.py on the host (fp32 run = the timed cpu_baseline sample; fp16-emulating run for the "
+                      "per-head deltas)",
+           "tolerance": {"box": 1e-3, "logit": "fp16 storage: p99.9 <= 2e-2 (north_star's 1e-4 is below one fp16 ulp)",
+                         "match": "box 2e-3 of the image size, score 4e-3, same label, two-sided"},
+           "match_frac": {"median": sorted(fr)[len(fr) // 2], "mean": sum(fr) / len(fr), "frames": len(fr),
+                          "renewal_flips_vs_fp32_oracle": flips, "T": T}}
+    # ---- post-processing on identical inputs
+    cap = max(1, T - 1) * N
+    B = len(ref)
+    ens_b = torch.empty((B, cap, 4), device=dev); ens_s = torch.empty((B, cap), device=dev)
+    ens_l = torch.empty((B, cap), device=dev, dtype=torch.int32)
+    steps = range(T - 1) if T > 1 else range(1)
+    topk_equal, want = True, [[] for _ in range(B)]
+    for j, si in enumerate(steps):
+        lg, bx = o32.trace[("logits", 0, si)], o32.trace[("coord", 0, si)]
+        ops.topk_scores(lg.to(dev).contiguous(), bx.to(dev).contiguous(), N, ens_b, ens_s, ens_l, j * N)
+        for i in range(B):
+            wb, ws, wl = om.topk_scores(lg[i], bx[i], N)
+            want[i].append((wb, ws, wl))
+            gb = ens_b[i, j * N:(j + 1) * N].cpu(); gl = ens_l[i, j * N:(j + 1) * N].cpu().long()
+            key = lambda b, l: sorted(zip(l.tolist(), map(tuple, b.tolist())))      # noqa: E731
+            topk_equal &= key(gb, gl) == key(wb, wl)
+    # NMS on the ORACLE's candidate lists (its boxes / scores / labels, bit for bit): keep order must be index-exact
+    for i in range(B):
+        ens_b[i] = torch.cat([e[0] for e in want[i]]).to(dev)
+        ens_s[i] = torch.cat([e[1] for e in want[i]]).to(dev)
+        ens_l[i] = torch.cat([e[2] for e in want[i]]).to(dev).int()
+    r = ops.nms(ens_b, ens_s, ens_l, thr=0.5, clip_wh=(float(w), float(h)))
+    cnt = r["count"].cpu().tolist()
+    nms_equal = True
+    for i in range(B):
+        fin = om.finalize_frame(torch.cat([e[0] for e in want[i]]), torch.cat([e[1] for e in want[i]]),
+                                torch.cat([e[2] for e in want[i]]), (w, h), True)
+        n = fin["scores"].numel()
+        nms_equal &= (cnt[i] == n and torch.equal(r["boxes"][i, :n].cpu(), fin["boxes"])
+                      and torch.equal(r["scores"][i, :n].cpu(), fin["scores"])
+                      and torch.equal(r["labels"][i, :n].cpu().long(), fin["labels"]))
+    out["keep_equal"] = {"topk_set_equal": bool(topk_equal), "nms_keep_order_equal": bool(nms_equal), "frames": B,
+                         "candidates_per_frame": cap}
+    # ---- per-head deltas on identical inputs vs the fp16-emulating oracle (2 frames)
+    Bt = min(2, L)
+    o16 = om.OracleDiffusionVID(sd, dict(num_proposals=N, sample_step=T), fp16=True, noise=om.NoiseSource(1234, N))
+    imgs = torch.cat([s["cur"] for s in samples[:Bt]])
+    feats = o16.backbone(imgs)
+    got_f = m.extract_features(imgs.to(dev))
+    fd = max(((g.float().permute(0, 3, 1, 2).cpu() - f).abs().max() / f.abs().max()).item() for g, f in zip(got_f, feats))
+    lv = ops.Levels([f.permute(0, 2, 3, 1).contiguous().half().to(dev) for f in feats])
+    whwh = torch.tensor([w, h, w, h], dtype=torch.float32)[None].expand(Bt, -1)
+    boxes = o16._x_to_boxes(om.NoiseSource(1234, N).get("img", 0, 0, 0, Bt), whwh)
+    temb = om.time_embedding(o16.c, torch.full((Bt,), 999, dtype=torch.long))
+    mem = o32.mem[0]
+    m._set_memory([mem.to(dev).contiguous(), None])
+    m._warm_constants([999])
+    dbox, dlog = [], []
+    pro = None
+    names = ["head.head_series.%d." % i for i in range(3)] + ["head.head_series_cond.0."]
+    for i, pre in enumerate(names):
+        cond = om.global_attention(o16.c, pro, mem, o16.cfg) if i == 3 else None
+        lg_r, bx_r, pro_r = om.rcnn_head(o16.c, pre, feats, boxes, pro, temb, o16.cfg, cond=cond)
+        e = m._pk["cond"][0] if i == 3 else m._pk["heads"][i]
+        p32 = None if pro is None else pro.to(dev).contiguous()
+        p16 = None if pro is None else pro.half().to(dev).contiguous()
+        shift = m._cond_shift(e, m._global_context(p16, Bt * N), Bt * N) if i == 3 else None
+        lg, bx, _, _ = m._head(e, lv, boxes.to(dev).contiguous(), p32, p16, 999, shift_rows=shift)
+        dbox.append((bx.cpu() - bx_r).abs() / size)
+        dlog.append((lg.cpu() - lg_r).abs())
+        boxes, pro = bx_r, pro_r
+    qb, ql = quantiles(torch.cat([d.flatten() for d in dbox])), quantiles(torch.cat([d.flatten() for d in dlog]))
+    out["box_delta"] = dict(qb, unit="fraction of the image size", heads=4, boxes=Bt * N, within_tolerance=qb["max"] <= 1e-3)
+    out["logit_delta"] = dict(ql, within_tolerance=ql["p999"] <= 2e-2)
+    out["feature_delta_rel_max"] = fd
+    return out
 
 
 def run_reference(args):
@@ -115,8 +253,10 @@ def run_reference(args):
         return
     k = max(1, args.steps)
     t0 = time.perf_counter()
-    _ = cpu_oracle_run(args, args.cpu_sample_frames, 1, max(0, min(args.warmup, 1)))[0] if args.warmup > 0 else None
-    fps, desc, times = cpu_oracle_run(args, args.cpu_sample_frames, 1, k)
+    fr_n, gl_n = cpu_sample_for_budget(args, k)
+    if args.warmup > 0:
+        cpu_oracle_run(args, fr_n, gl_n, 1)
+    fps, desc, times, _ = cpu_oracle_run(args, fr_n, gl_n, k)
     ms = 1000.0 * statistics.mean(times)
     line = {"impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": k, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -230,7 +370,29 @@ def run_clip(model, samples, to_host):
     return n_out, d2h
 
 
-def timed(model, samples, steps, to_host, dist, dev):
+def run_clip_engine(model, samples, dev):
+    """The clip through the reference's own loop body (mega_core/engine/inference.py:26-93 with its timer): move `cur`
+    and every ref ImageList to the device (:35-40), call the model, torch.cuda.synchronize() (:70-73), outputs to the
+    CPU (:75), store (:91-93)."""
+    n_out = 0
+    results = {}
+    cpu = torch.device("cpu")
+    for i, s in enumerate(samples):
+        images = dict(s)
+        images["cur"] = images["cur"].to(dev)
+        for key in ("ref_l", "ref_g"):
+            images[key] = [img.to(dev) for img in images[key]]
+        out = model(images)
+        torch.cuda.synchronize()
+        out = [o.to(cpu) for o in out]
+        results.update({i + j: o for j, o in enumerate(out)})
+        n_out += len(out)
+    for bl in results.values():
+        assert bl.bbox.shape[0] == bl.get_field("scores").shape[0]
+    return n_out, 0
+
+
+def timed(model, samples, steps, to_host, dist, dev, runner=None):
     from diffusionvid_b200 import ops
     if dist:
         torch.distributed.barrier()
@@ -241,7 +403,7 @@ def timed(model, samples, steps, to_host, dist, dev):
     frames = 0
     d2h = 0
     for _ in range(steps):
-        n, b = run_clip(model, samples, to_host)
+        n, b = runner(model, samples, dev) if runner else run_clip(model, samples, to_host)
         frames += n
         d2h += b
     e1.record()
@@ -305,7 +467,40 @@ def run_ours(args):
         h2d_u8 = (m.io_bytes["h2d"] - io1["h2d"]) // max(1, args.steps)
         d2h_u8 = (m.io_bytes["d2h"] - io1["d2h"]) // max(1, args.steps)
         del u8_samples
+        # the reference's engine loop verbatim (uploads of cur + refs per call, a device synchronisation per call)
+        for _ in range(2):
+            run_clip_engine(m, host_samples, dev)
+        io2 = dict(m.io_bytes)
+        ms_eng, frames_eng, _, _ = timed(m, host_samples, args.steps, True, dist, dev, runner=run_clip_engine)
+        img_bytes = host_samples[0]["cur"].tensors.numel() * host_samples[0]["cur"].tensors.element_size()
+        n_moved = sum(1 + len(s["ref_l"]) + len(s["ref_g"]) for s in host_samples)
+        d2h_eng = (m.io_bytes["d2h"] - io2["d2h"]) // max(1, args.steps)
         m.host_results = False
+
+        # N > 1: the SAME clip dealt frame by frame to the ranks (BASELINE config 5)
+        fs = None
+        if dist and not shard_frames and not args.no_frame_sharded:
+            m.set_frame_sharding(rank, world)
+            for _ in range(2):
+                run_clip(m, dev_samples, False)
+            cb0, ne0 = dict(m.comm_bytes), len(m.comm_events)
+            ms_fs, frames_fs, _, _ = timed(m, dev_samples, args.steps, False, dist, dev)
+            ag_us = [1000.0 * a.elapsed_time(b) for a, b in m.comm_events[ne0:]]
+            fs = {"value": frames_fs / (ms_fs / 1000.0), "unit": "frames/s", "scaling": "strong",
+                  "ms_per_step": ms_fs / args.steps,
+                  "memory_allgather_bytes_per_video": (m.comm_bytes["memory"] - cb0["memory"]) // max(1, args.steps),
+                  "memory_allgather_us": statistics.median(ag_us) if ag_us else None,
+                  "results_allgather_bytes_per_step": (m.comm_bytes["results"] - cb0["results"]) // max(1, args.steps),
+                  "collectives_per_step": "1 all-gather of memory candidates per video + 1 all-gather of detections "
+                                          "per key batch (NCCL)"}
+            m.set_frame_sharding(rank, 1)
+
+        # device time of the captured execution units in a normal (graph-replayed) pass of the clip
+        m.unit_events = {}
+        run_clip(m, dev_samples, False)
+        torch.cuda.synchronize()
+        units = {k: [a.elapsed_time(b) for a, b in v] for k, v in m.unit_events.items()}
+        m.unit_events = None
 
         roof = None
         if rank == 0 and not args.no_roofline:
@@ -353,6 +548,26 @@ def run_ours(args):
                                         "frac": rd["gbs"] / peak_bw, "launches_per_step": rd["launches"],
                                         "avg_launch_us": 1000.0 * rd["ms"] / max(1, rd["launches"]),
                                         "share_of_step": rd["ms"] / clip_ms if clip_ms > 0 else None}
+            dec = units.get(("decode", hp["infer_batch"]))
+            if dec and args.backbone == "r101":
+                # one head evaluation at M = 8 x 300 boxes = 72.6 GFLOP and 82 MB of algorithmic bytes
+                # (feature pyramids 52.3 MB + head weights 27.4 MB + object features / boxes, each tensor once, the
+                # generated DynamicConv weights NOT counted: fused they never leave the chip); global attention 3.1 GF
+                evals = args.T * 4 if args.T > 1 else 1
+                dms = statistics.median(dec)
+                gf = evals * 72.6 * args.proposals / 300.0 + args.T * 3.1
+                roof["decoder_step"] = {
+                    "kernel": "decode unit of one 8-frame key batch: %d head evaluations (ROIAlign + self-attention + "
+                              "DynamicConv + FFN + towers + apply_deltas) + %d global attentions + DDIM + top-k + NMS, "
+                              "one CUDA-graph replay timed with CUDA events" % (evals, args.T),
+                    "unit_ms": dms, "head_eval_us": 1000.0 * dms / evals, "bound": "tensor",
+                    "achieved": gf / dms, "peak": peak_tf, "unit": "TFLOP/s", "frac": gf / dms / peak_tf,
+                    "hbm": {"algorithmic_bytes_per_head_eval": 82e6, "achieved_gbs": 82e6 * evals / dms / 1e6,
+                            "peak_gbs": peak_bw, "frac": 82e6 * evals / dms / 1e6 / peak_bw},
+                    "roi_dynconv_kernel": roof.pop("decoder_step", None)}
+            ext = units.get(("extract", hp["infer_batch"])) or units.get(("features", hp["infer_batch"]))
+            if ext:
+                roof["extract_unit_ms"] = statistics.median(ext)
             tf = os.path.join(ROOT, "profiles", "conv_gemm_traffic.json")
             if os.path.exists(tf):       # dram bytes per launch from the committed ncu --set full capture
                 with open(tf) as f:
@@ -365,14 +580,21 @@ def run_ours(args):
     value = total_frames / (ms / 1000.0)
     e2e_value = frames_e2e * mult / (ms_e2e / 1000.0)
     e2e_u8_value = frames_u8 * mult / (ms_u8 / 1000.0)
+    e2e_eng_value = frames_eng * mult / (ms_eng / 1000.0)
+    if fs is not None:
+        fs["efficiency_vs_video_sharded"] = fs["value"] / value       # value = N x the un-sharded per-GPU rate
+        fs["speedup_vs_one_gpu"] = fs["value"] / (value / world)
     if rank != 0:
         if dist:
             torch.distributed.destroy_process_group()
         return
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        fps, desc, _ = cpu_oracle_run(args, args.cpu_sample_frames, 1, 1)
+    cpu = parity = None
+    if not args.no_cpu_baseline and world == 1 and args.backbone == "r101":
+        fps, desc, _, pack = cpu_oracle_run(args, args.cpu_sample_frames, args.cpu_sample_global, 1)
         cpu = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sample": desc}
+        if not args.no_parity:
+            with torch.no_grad():
+                parity = parity_report(args, dev, pack)
     line = {"metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if shard_frames else "weak",
@@ -395,7 +617,13 @@ def run_ours(args):
                        "d2h_bytes_per_step": d2h_u8, "ms_per_step": ms_u8 / args.steps,
                        "input": "uint8 ImageLists in pinned host memory (decoded frames; ToTensor fused into "
                                 "dvid_preprocess_u8) - same public call"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+            "e2e_engine": {"value": e2e_eng_value, "unit": "frames/s", "ms_per_step": ms_eng / args.steps,
+                           "h2d_bytes_per_step": n_moved * img_bytes, "d2h_bytes_per_step": d2h_eng,
+                           "loop": "mega_core/engine/inference.py:26-93 verbatim: cur + every ref ImageList .to(device) "
+                                   "per call (:35-40; cur is a second upload of a frame that also arrives as a ref), "
+                                   "model(images), torch.cuda.synchronize() per call (:70-73), outputs .to(cpu) (:75)"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+            "frame_sharded": fs}
     print(json.dumps(line))
     if dist:
         torch.distributed.destroy_process_group()

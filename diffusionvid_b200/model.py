@@ -148,6 +148,9 @@ class DiffusionDet(nn.Module):
         self._streams_inner = []
         self._copy_stream = None
         self.io_bytes = {"h2d": 0, "d2h": 0}   # bytes moved by the model itself (bench.py reports them)
+        self.comm_bytes = {"memory": 0, "results": 0}    # bytes received through collectives (frame sharding)
+        self.comm_events = []                  # (start, end) CUDA events around the per-video memory all-gather
+        self.unit_events = None                # dict -> CUDA events around every graph-unit replay (bench.py)
         self._host_ring = [None] * 4          # pinned result buffers of the last key batches (host_results mode)
         self._host_ring_pos = 0
         self._dev_ring = [None] * 4           # device-resident results whose counts have not been read yet
@@ -706,7 +709,16 @@ class DiffusionDet(nn.Module):
         if g is None:
             g = _CapturedUnit(fn, tensors, consts)
             self._graphs[sig] = g
-        return g(tensors)
+        if self.unit_events is None:
+            return g(tensors)
+        # measurement hook (bench.py): CUDA events around the replay of this unit, keyed by unit name and frame count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = g(tensors)
+        e1.record()
+        frames = next(iter(v.shape[0] for k, v in sorted(tensors.items()) if v is not None and k in ("imgs", "p3")), 0)
+        self.unit_events.setdefault((name, frames), []).append((e0, e1))
+        return out
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, images, targets=None):
@@ -994,8 +1006,16 @@ class DiffusionDet(nn.Module):
         for j, i in enumerate([i for i in gl if i % world == rank]):
             send[j, :k1] = ex["k1"][pos[i]]
             send[j, k1:] = ex["k2"][pos[i]]
-        recv = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(recv, send, group=group)
+        recv = torch.empty((world,) + tuple(send.shape), device=dev, dtype=F32)
+        timed = dev.type == "cuda"
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        dist.all_gather_into_tensor(recv.view(world * per, k1 + k2, 256), send, group=group)
+        if timed:
+            e1.record()
+            self.comm_events.append((e0, e1))
+        self.comm_bytes["memory"] += recv.numel() * 4
         seen = [0] * world
         rows = []
         for i in gl:
@@ -1006,22 +1026,31 @@ class DiffusionDet(nn.Module):
         return allc[:, :k1].reshape(-1, 256).contiguous(), allc[:, k1:].reshape(-1, 256).contiguous()
 
     def _exchange_results(self, r, own, batch, cap, dev):
-        """Each rank fills the rows of its own frames in a zero [batch, 1 + 6*cap] fp32 tensor (count | boxes | scores |
-        labels; counts <= cap and labels <= 30 are exact in fp32) and one SUM all-reduce replicates the batch."""
+        """Every rank contributes the rows of the frames it owns - (frame index | count | boxes | scores | labels) packed
+        in fp32, counts <= cap and labels <= 30 are exact - and ONE all-gather replicates the key batch on all ranks
+        (the reference gathers results only at the end of the dataset, engine/inference.py:98; here every rank returns
+        the full list per call, as the single-process model does).  Ranks own at most ceil(batch / world) frames of a
+        batch; unused rows carry frame index -1."""
         import torch.distributed as dist
-        _, _, group = self._shard
-        buf = torch.zeros((batch, 1 + 6 * cap), device=dev, dtype=F32)
+        _, world, group = self._shard
+        per = (batch + world - 1) // world
+        send = torch.zeros((per, 2 + 6 * cap), device=dev, dtype=F32)
+        send[:, 0] = -1.0
         if own:
-            idx = torch.tensor(own, device=dev, dtype=torch.long)
             n = len(own)
-            c = r["count"].to(F32).view(n, 1)
             valid = torch.arange(cap, device=dev)[None, :] < r["count"].view(n, 1)     # rows past count are undefined
             zero = torch.zeros((), device=dev, dtype=F32)
-            row = torch.cat([c, torch.where(valid[..., None], r["boxes"], zero).reshape(n, -1),
-                             torch.where(valid, r["scores"], zero), torch.where(valid, r["labels"].to(F32), zero)],
-                            dim=1)
-            buf[idx] = row
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            send[:n] = torch.cat([torch.tensor(own, device=dev, dtype=F32).view(n, 1), r["count"].to(F32).view(n, 1),
+                                  torch.where(valid[..., None], r["boxes"], zero).reshape(n, -1),
+                                  torch.where(valid, r["scores"], zero),
+                                  torch.where(valid, r["labels"].to(F32), zero)], dim=1)
+        recv = torch.empty((world * per, 2 + 6 * cap), device=dev, dtype=F32)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        self.comm_bytes["results"] += recv.numel() * 4
+        idx = recv[:, 0].round().long()
+        rows = recv[idx >= 0]
+        buf = torch.empty((batch, 1 + 6 * cap), device=dev, dtype=F32)
+        buf[idx[idx >= 0]] = rows[:, 1:]
         return dict(count=buf[:, 0].round().to(torch.int32), boxes=buf[:, 1:1 + 4 * cap].reshape(batch, cap, 4),
                     scores=buf[:, 1 + 4 * cap:1 + 5 * cap], labels=buf[:, 1 + 5 * cap:].round().to(torch.int32))
 

@@ -22,9 +22,12 @@ size), 1e-4 class logit "fp16 tolerance", bit-exact NMS index order):
      checked bit-for-bit at operator level in tests/test_gpu_ops.py).
   B  test_postprocessing_identical_inputs_*  - top-k / NMS keep SETS AND ORDER are equal (bit-exact indices, boxes,
      labels, scores) when both implementations are fed the same logits / boxes of a full T = 4 ensemble.
-  C  test_clip_free_running_*  - the whole state machine free-running on both sides; every mismatch is attributed to
-     its class with counts (FPN-level flips, renewal 0.5-threshold flips, FPS picks), the first-step (t = 999) deltas
-     - upstream of every feedback loop - are asserted, and the final detections are compared two-sidedly.
+  C  test_clip_free_running_*  - the whole state machine free-running on both sides, final detections compared
+     two-sidedly.  T = 1 must agree (median and mean >= 0.95 at 2e-3 box / 4e-3 score).  For T > 1 the algorithm itself is
+     discontinuous - one renewal decision (sigmoid(max logit) vs 0.5) that differs re-deals the step noise of every
+     later box of that frame - so every mismatch is attributed with counts: FPS picks, renewal flips per frame, and each
+     DDIM step is repeated with the ORACLE's state (x_t, memory) as input, where boxes pooled from the same FPN levels
+     must again be within 1e-3 / 2e-2 and level flips are counted; frames without a renewal flip must match.
 """
 import json
 import os
@@ -34,7 +37,7 @@ import torch
 
 from diffusionvid_b200 import model as pm, ops, structures, synth
 from oracle import model as om, ops as oo
-from tests.parity_util import match_fraction_two_sided
+from tests.parity_util import match_fraction_two_sided, oracle_step, product_step, quantiles as _q, step_deltas
 
 pytestmark = pytest.mark.gpu
 
@@ -80,13 +83,6 @@ def _build(T, swin=None, seed=1234):
     dsd = {k: v.detach().to("cuda") for k, v in sd.items()}
     o = om.OracleDiffusionVID(dsd, ocfg, fp16=True, noise=noise)
     return hp, m, o, noise
-
-
-def _q(d):
-    d = d.flatten().float()
-    qs = torch.quantile(d[torch.randperm(d.numel(), device=d.device)[:4_000_000]] if d.numel() > 4_000_000 else d,
-                        torch.tensor([0.5, 0.99, 0.999], device=d.device))
-    return dict(p50=qs[0].item(), p99=qs[1].item(), p999=qs[2].item(), max=d.max().item())
 
 
 def _save_report():
@@ -207,6 +203,7 @@ def _free_running(cuda, T, swin, tag):
     m.debug_trace = True
     ib, N = hp["infer_batch"], hp["num_proposals"]
     L, G = ib, 24
+    size = max(H_IMG, W_IMG)
     frames = synth.make_clip(L + G, H_IMG, W_IMG, seed=1234).to(cuda)
     samples = synth.clip_samples(frames[:L], [], H_IMG, W_IMG, infer_batch=ib, max_offset=ib - 1)
     s0 = samples[0]
@@ -219,7 +216,7 @@ def _free_running(cuda, T, swin, tag):
                      frame_id=0, start_id=0, end_id=L - 1, seg_len=L, frame_category=0, video_id=0))
     assert len(got) == len(ref) == L
     rep = {}
-    # global memory: same rows picked by the 1800 -> 900 farthest-point sampling?
+    # ---- global memory: same rows picked by the 1800 -> 900 farthest-point sampling?
     pm_mem, o_mem = m.proposal_feats_global[0].float(), o.mem[0].float()
     assert pm_mem.shape == o_mem.shape == (hp["mem_size"], 256)
     d = torch.cdist(pm_mem, o_mem)
@@ -228,43 +225,84 @@ def _free_running(cuda, T, swin, tag):
     same_slot = (d.diagonal() <= 1.0).float().mean().item()
     in_set = (d.min(dim=1)[0] <= 1.0).float().mean().item()
     rep["memory"] = dict(rows=hp["mem_size"], same_pick_same_slot=same_slot, same_pick_any_slot=in_set)
-    # per-step deltas of the final-stage outputs; step 0 is upstream of every DDIM feedback
+    # ---- free-running per-step deltas of the final-stage outputs + the discrete decisions that separate the runs
     tr, otr = m.last_trace, o.trace
+    flips_per_frame = torch.zeros(L, dtype=torch.long)
     for si in range(T):
         lg, bx = tr[("logits", 0, si, 0)], tr[("coord", 0, si, 0)]
         lg_r, bx_r = otr[("logits", 0, si)], otr[("coord", 0, si)]
         keep_p = torch.sigmoid(lg).max(-1)[0] > 0.5
         keep_o = torch.sigmoid(lg_r).max(-1)[0] > 0.5
-        rep["step%d" % si] = dict(box=_q((bx - bx_r).abs() / max(H_IMG, W_IMG)), logit=_q((lg - lg_r).abs()),
-                                  renewal_flips=int((keep_p != keep_o).sum().item()), boxes=int(keep_p.numel()),
-                                  level_flips_final_boxes=int((_levels(bx) != _levels(bx_r)).sum().item()))
+        if si < T - 1:                                       # the last step's keep mask is never used (:573-575)
+            flips_per_frame += (keep_p != keep_o).sum(dim=1).cpu()
+        rep["free_step%d" % si] = dict(box=_q((bx - bx_r).abs() / size), logit=_q((lg - lg_r).abs()),
+                                       renewal_flips=int((keep_p != keep_o).sum().item()), boxes=int(keep_p.numel()))
     fr, counts_equal = [], 0
     for g, r in zip(got, ref):
         counts_equal += int(len(g) == r["scores"].numel())
         fr.append(match_fraction_two_sided(g.bbox.cpu(), g.get_field("scores").cpu(), g.get_field("labels").cpu(),
-                                           r["boxes"].cpu(), r["scores"].cpu(), r["labels"].cpu(), max(H_IMG, W_IMG),
+                                           r["boxes"].cpu(), r["scores"].cpu(), r["labels"].cpu(), size,
                                            box_tol=2e-3, score_tol=4e-3))
+    clean = [f for f, n in zip(fr, flips_per_frame.tolist()) if n == 0]
     rep["detections"] = dict(frames=L, match_two_sided=fr, counts_equal=counts_equal,
-                             median=sorted(fr)[len(fr) // 2], mean=sum(fr) / len(fr))
+                             median=sorted(fr)[len(fr) // 2], mean=sum(fr) / len(fr),
+                             renewal_flips_per_frame=flips_per_frame.tolist(),
+                             frames_without_renewal_flip=len(clean), match_of_those=clean)
+    # ---- every DDIM step again with the ORACLE's state as input (x_t, memory): what is left is the arithmetic inside
+    # one step plus the FPN-level decisions between its heads, which are counted and separated out
+    feats = [torch.cat([o.feats[i][l] for i in range(L)]) for l in range(3)]
+    lv = ops.Levels([f.permute(0, 2, 3, 1).contiguous().half() for f in feats])
+    whwh = torch.tensor([W_IMG, H_IMG, W_IMG, H_IMG], dtype=torch.float32, device=cuda)[None].expand(L, -1)
+    times = list(reversed(torch.linspace(-1, 999, steps=T + 1).int().tolist()))[:-1]
+    with torch.no_grad():
+        m._set_memory([o.mem[0].contiguous(), o.mem[1]])
+        m._warm_constants(times)
+        for si, t in enumerate(times if T > 1 else []):
+            x = noise.get("img", 0, 0, 0, L).to(cuda) if si == 0 else otr[("img", 0, si - 1)]
+            boxes = o._x_to_boxes(x, whwh)
+            po = product_step(m, lv, boxes, t, L, N)
+            oo_ = oracle_step(om, o, feats, boxes, t, L, o.mem[0])
+            per_head = step_deltas(po, oo_, lambda b: oo.assign_levels(b, 3, 5), size)
+            rep["forced_step%d" % si] = per_head
     REPORT["free_running_" + tag] = rep
     _save_report()
     print("PARITY_C " + tag + " " + json.dumps(rep))
     return rep
 
 
+def _check_forced_steps(rep, T):
+    for si in range(T if T > 1 else 0):
+        for h, st in enumerate(rep["forced_step%d" % si]):
+            # boxes that were pooled from the same FPN levels in both implementations: arithmetic differences only
+            assert st["box_same_level"]["p999"] <= 1e-3, (si, h, st)
+            assert st["logit_same_level"]["p999"] <= 2e-2, (si, h, st)
+            assert st["level_flips_so_far"] <= 0.01 * 2400, (si, h, st)
+
+
 @pytest.mark.parametrize("T", [1, 4])
 def test_clip_free_running_r101(cuda, T, oracle_on_device):
     rep = _free_running(cuda, T, None, "r101_T%d" % T)
-    s0 = rep["step0"]
-    # first step: three base heads on identical noise boxes + the conditioned head on the FPS memory
+    s0 = rep["free_step0"]
+    # first step, free running: three base heads on identical noise boxes + the conditioned head on the FPS memory
     assert s0["box"]["p50"] <= 1e-3 and s0["box"]["p99"] <= 4e-3, s0
     assert s0["logit"]["p50"] <= 5e-3, s0
     assert rep["memory"]["same_pick_any_slot"] >= 0.9, rep["memory"]
-    assert rep["detections"]["median"] >= 0.9, rep["detections"]
+    _check_forced_steps(rep, T)
+    det = rep["detections"]
+    if T == 1:
+        assert det["median"] >= 0.95 and det["mean"] >= 0.95, det
+    else:
+        # T > 1: ONE renewal decision that differs (sigmoid(max logit) vs 0.5, diffusion_det.py:559-572) re-deals the
+        # step noise of every later box of that frame (:585-596 compacts the kept boxes before drawing), so a frame
+        # either follows the oracle or departs from it as a whole; frames without such a flip must agree
+        assert all(f >= 0.8 for f in det["match_of_those"]), det
+        assert det["median"] >= 0.5, det
 
 
 def test_clip_free_running_swin_b(cuda, oracle_on_device):
     rep = _free_running(cuda, 4, SWIN_B, "swin_b_T4")
-    s0 = rep["step0"]
+    s0 = rep["free_step0"]
     assert s0["box"]["p50"] <= 1e-3 and s0["box"]["p99"] <= 4e-3, s0
-    assert rep["detections"]["median"] >= 0.9, rep["detections"]
+    _check_forced_steps(rep, 4)
+    det = rep["detections"]
+    assert all(f >= 0.8 for f in det["match_of_those"]), det
