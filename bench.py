@@ -447,9 +447,11 @@ def run_ours(args):
     host_samples, h2d_bytes = make_clip_inputs(args, dev, pinned=True)
 
     with torch.no_grad():
+        # the clock sampler starts BEFORE the warm-up: nvidia-smi's start-up takes driver locks that stall kernel
+        # launches for ~0.1 s, which must not fall into a timed region of a few hundred ms
+        sampler = ClockSampler(local) if rank == 0 else None
         for _ in range(max(3, args.warmup)):
             run_clip(m, dev_samples, False)
-        sampler = ClockSampler(local) if rank == 0 else None
         ms, frames, launches, _ = timed(m, dev_samples, args.steps, False, dist, dev)
         clocks = sampler.stop() if sampler else None
         m.host_results = True      # e2e: detections are delivered on the host (one packed D2H copy per key batch)

@@ -929,6 +929,13 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     if (env_bn < 0) { const char* e = getenv("DVID_FORCE_BN"); env_bn = e ? atoi(e) : 0; }
     if (bn == 0 && env_bn > 0 && cout >= env_bn) bn = env_bn;
   }
+  // Batch invariance (a frame's result must not depend on how many other frames share the launch): the
+  // tile WIDTH may follow the tile count - every output element is accumulated over K in the same k-block order for any
+  // width - but the way a same-resolution residual is added may not: >= 128-wide tiles add it through the tensor core
+  // (identity MMA into the accumulator, before the bias), 64-wide tiles in the epilogue registers (after the bias), and
+  // the two round differently.  So convolutions with such a residual never take the 64-wide tile.
+  const bool res_same = resid != nullptr && resid_shift == 0 && out != nullptr && cout >= 128;
+  if (res_same && bn == 64) bn = 128;
   static int cost_model = -1;
   if (cost_model < 0) { const char* e = getenv("DVID_BN_COST"); cost_model = e ? atoi(e) : 1; }
   if (bn == 0 && cost_model) {
@@ -941,6 +948,7 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     double best = 1e30;
     for (int i = 0; i < 3; ++i) {
       if (cand[i] > 64 && cout < cand[i]) continue;
+      if (res_same && cand[i] < 128) continue;
       const long long tiles = static_cast<long long>(p.m_tiles) * p.splits * ((cout + cand[i] - 1) / cand[i]);
       const long long waves = (tiles + num_sms() - 1) / num_sms();
       const double c = static_cast<double>(waves) * tile_cost[i];
@@ -953,6 +961,7 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     else if (cout >= 128 && static_cast<long long>(p.m_tiles) * p.splits * ((cout + 127) / 128) >= want) bn = 128;
     else bn = (cout >= 256 && p.m_tiles * p.splits >= 16) ? 128 : 64;
     if (cout <= 64) bn = 64;
+    if (res_same && bn == 64) bn = 128;
   }
   if (bn != 64 && bn != 128 && bn != 256) return DVID_ERR_SHAPE;
   p.n_tiles = (cout + bn - 1) / bn;

@@ -13,6 +13,7 @@
 //   roi_align_kernel      : ROI tile -> global (and the per-box mean that seeds pro_features, box_head.py:509-510)
 //   roi_dynconv_kernel<G> : G=false gathers the ROI tile itself (fused ROIAlign), G=true reads it from global.
 #include <stdlib.h>
+#include "ptx_sm100.cuh"
 #include "dvid_internal.h"
 #include "warp_mma.cuh"
 
@@ -501,6 +502,258 @@ roi_dynconv_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ tcgen05 DynamicConv
+// Same operation as roi_dynconv_kernel with the two per-box contractions on the 5th-generation tensor cores:
+//   bmm1  F1[49x64]  = ROI[49x256] . P1[256x64]   one tcgen05.mma chain M=128 (rows >= 64 are don't-care, see below),
+//                                                 N=64, K=256, accumulator in TMEM columns 0..63
+//   LN(64)+ReLU      straight out of TMEM (tcgen05.ld), written back to shared memory as the next A operand
+//   bmm2  F2[49x256] = F1[49x64] . P2[64x256]     M=128, N=256, K=64, accumulator in TMEM columns 0..255
+//   LN(256)+ReLU     out of TMEM -> staging tile -> coalesced global store
+// Operands are K-major, 128-byte swizzled (the layout umma_desc_sw128_kmajor describes):
+//   ROI tile   4 k-blocks x [64 rows][128 B], written by the gather warps (st.shared + fence.proxy.async)
+//   P1^T       4 k-blocks x [64 rows (j)][128 B (64 i)]   TMA, box {64,64,1} of the 3-D view [box][j][i]
+//   P2^T       [256 rows (i)][128 B (64 j)]               TMA, box {64,256,1} of the 3-D view [box][i][j]
+// so the generated weights arrive TRANSPOSED from the dynamic_layer GEMM: the rows of its weight matrix are permuted
+// once at pack time (params[j*256+i] = P1[i][j], params[16384+i*64+j] = P2[j][i]; box_head.py:693-696 layout otherwise).
+// A tcgen05 tile has at least 64 rows in the documented lane layout only for M=128, so every box is issued as an
+// M=128 tile whose upper 64 rows read whatever follows the operand in shared memory (the next k-block / the next
+// buffer, always inside the CTA's allocation); rows are independent in a GEMM, TMEM lanes 64..127 are never read.
+// One box per CTA, two CTAs per SM (each allocates 256 TMEM columns), 8 warps: all gather, warp 1 issues the MMAs,
+// warps 0,1,4,5 (TMEM sub-partitions 0 and 1 = lanes 0..63) run the two LayerNorm epilogues, all store.
+constexpr int TC_ROI = 0;                       // 4 x 8 KB; reused as the [64][512 B] output staging tile
+constexpr int TC_P1 = TC_ROI + 4 * 8192;        // 4 x 8 KB
+constexpr int TC_F1 = TC_P1 + 4 * 8192;         // 8 KB
+constexpr int TC_P2 = TC_F1 + 8192;             // 32 KB (also the don't-care rows of the F1 operand)
+constexpr int TC_LN = TC_P2 + 32768;            // gamma2 | beta2 (256 floats each)
+constexpr int TC_STAT = TC_LN + 2 * 256 * 4;    // [2 halves][64 rows] float2
+constexpr int TC_BAR = TC_STAT + 2 * 64 * 8;    // mbarriers + tmem slot
+constexpr int TC_TOTAL = TC_BAR + 64 + 1024;    // + alignment slack
+
+struct DynMaps {
+  CUtensorMap p1;
+  CUtensorMap p2;
+};
+
+template <bool kRoiFromGlobal>
+__global__ void __launch_bounds__(256, 2)
+roi_dynconv_tc_kernel(const __grid_constant__ DynMaps maps, RoiLevels lv, const float* __restrict__ boxes,
+                      int boxes_per_frame, const __half* __restrict__ roi_in,
+                      const float* __restrict__ g1, const float* __restrict__ b1,
+                      const float* __restrict__ g2, const float* __restrict__ b2, __half* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sRoi = smem + TC_ROI;
+  uint8_t* sP1 = smem + TC_P1;
+  uint8_t* sF1 = smem + TC_F1;
+  uint8_t* sP2 = smem + TC_P2;
+  float* sG2 = reinterpret_cast<float*>(smem + TC_LN);
+  float* sB2 = sG2 + 256;
+  float2* sStat = reinterpret_cast<float2*>(smem + TC_STAT);
+  uint64_t* p1_full = reinterpret_cast<uint64_t*>(smem + TC_BAR);
+  uint64_t* p2_full = p1_full + 1;
+  uint64_t* mma_bar = p1_full + 2;
+  uint64_t* f1_ready = p1_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p1_full + 4);
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&maps.p1);
+    tma_prefetch_desc(&maps.p2);
+    mbar_init(p1_full, 1);
+    mbar_init(p2_full, 1);
+    mbar_init(mma_bar, 1);
+    mbar_init(f1_ready, 128);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  // ---- the box's generated weights: TMA into the swizzled operand layouts
+  if (warp == 1 && elect_one()) {
+    mbar_expect_tx(p1_full, 4 * 8192);
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) tma_load_3d(sP1 + kb * 8192, &maps.p1, p1_full, kb * 64, 0, b);
+    mbar_expect_tx(p2_full, 32768);
+    tma_load_3d(sP2, &maps.p2, p2_full, 0, 0, b);
+  }
+  sG2[tid] = __ldg(g2 + tid);
+  sB2[tid] = __ldg(b2 + tid);
+
+  // ---- ROI tile -> A operand: row = bin, 16-byte chunk c of the 256 channels -> k-block c/8, chunk (c%8)^(row%8)
+  auto roi_dst = [&](int row, int c) -> uint8_t* {
+    return sRoi + (c >> 3) * 8192 + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+  };
+  if (kRoiFromGlobal) {
+    const uint4* r = reinterpret_cast<const uint4*>(roi_in + static_cast<long>(b) * NBIN * D);
+    for (int id = tid; id < NBIN * 32; id += 256) *reinterpret_cast<uint4*>(roi_dst(id >> 5, id & 31)) = __ldg(r + id);
+  } else {
+    __shared__ __align__(16) TapTable taps;
+    const RoiGeom gm = roi_geometry(lv, boxes, b, boxes_per_frame);
+    build_tap_table(gm, taps, tid);
+    __syncthreads();
+    for (int bin = warp; bin < NBIN; bin += 8) {
+      float acc[8];
+      roi_bin_table(gm, taps, bin, lane, acc);
+      *reinterpret_cast<uint4*>(roi_dst(bin, lane)) = pack8(acc);
+    }
+  }
+  fence_proxy_async_smem();     // the tensor core reads the tile through the async proxy
+  __syncthreads();
+
+  const bool epi = (warp & 3) < 2;            // warps 0,1,4,5: TMEM lanes 0..63
+  const int q = warp & 3;                     // TMEM sub-partition
+  const int half = warp >> 2;                 // column half owned by this thread
+  const int r = q * 32 + lane;                // row of the tile == TMEM lane (epilogue warps only)
+  const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+  if (warp == 1) {
+    // ===================== MMA issue: bmm1 =====================
+    mbar_wait(p1_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(128, DD);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(sRoi + kb * 8192));
+        const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(sP1 + kb * 8192));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+      }
+      umma_commit(mma_bar);
+    }
+    __syncwarp();
+  }
+  if (epi) {
+    // ===================== LayerNorm(64) + ReLU -> F1 operand =====================
+    mbar_wait(mma_bar, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld32(tlane + half * 32, v);
+    tmem_ld_wait();
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = __uint_as_float(v[j]);
+      sum += a;
+      sq = fmaf(a, a, sq);
+    }
+    sStat[half * 64 + r] = make_float2(sum, sq);
+    named_bar_sync(1, 128);
+    const float2 other = sStat[(half ^ 1) * 64 + r];
+    const float mean = (sum + other.x) * (1.f / DD);
+    const float rstd = rsqrtf(fmaxf((sq + other.y) * (1.f / DD) - mean * mean, 0.f) + 1e-5f);
+    uint8_t* rowp = sF1 + r * 128;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int col = half * 32 + c4 * 8 + e;
+        y[e] = fmaxf((__uint_as_float(v[c4 * 8 + e]) - mean) * rstd * __ldg(g1 + col) + __ldg(b1 + col), 0.f);
+      }
+      uint4 pk;
+      pk.x = pack_half2(y[0], y[1]);
+      pk.y = pack_half2(y[2], y[3]);
+      pk.z = pack_half2(y[4], y[5]);
+      pk.w = pack_half2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(rowp + (((half * 4 + c4) ^ (r & 7)) << 4)) = pk;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(f1_ready);
+  }
+  if (warp == 1) {
+    // ===================== MMA issue: bmm2 (the F1 accumulator columns are drained: f1_ready) =====================
+    mbar_wait(f1_ready, 0);
+    mbar_wait(p2_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_f16(128, D);
+      const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(sF1));
+      const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(sP2));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+      umma_commit(mma_bar);
+    }
+    __syncwarp();
+  }
+  if (epi) {
+    // ===================== LayerNorm(256) + ReLU -> staging tile (the ROI buffer, plain swizzled rows) =====================
+    mbar_wait(mma_bar, 1);
+    tc_fence_after();
+    const uint32_t tcol = tlane + half * 128;
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tcol + c2 * 64, v0);
+      tmem_ld32(tcol + c2 * 64 + 32, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float a = __uint_as_float(v0[j]), c = __uint_as_float(v1[j]);
+        sum += a + c;
+        sq = fmaf(a, a, sq);
+        sq = fmaf(c, c, sq);
+      }
+    }
+    sStat[half * 64 + r] = make_float2(sum, sq);
+    named_bar_sync(1, 128);
+    const float2 other = sStat[(half ^ 1) * 64 + r];
+    const float mean = (sum + other.x) * (1.f / D);
+    const float rstd = rsqrtf(fmaxf((sq + other.y) * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      uint32_t vv[2][32];
+      tmem_ld32(tcol + c2 * 64, vv[0]);
+      tmem_ld32(tcol + c2 * 64 + 32, vv[1]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int col = half * 128 + c2 * 64 + h * 32 + c4 * 8;
+          const float4 ga = *reinterpret_cast<const float4*>(sG2 + col), gb = *reinterpret_cast<const float4*>(sG2 + col + 4);
+          const float4 ba = *reinterpret_cast<const float4*>(sB2 + col), bb = *reinterpret_cast<const float4*>(sB2 + col + 4);
+          const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+          const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          float y[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            y[e] = fmaxf((__uint_as_float(vv[h][c4 * 8 + e]) - mean) * rstd * gg[e] + be[e], 0.f);
+          uint4 pk;
+          pk.x = pack_half2(y[0], y[1]);
+          pk.y = pack_half2(y[2], y[3]);
+          pk.z = pack_half2(y[4], y[5]);
+          pk.w = pack_half2(y[6], y[7]);
+          *reinterpret_cast<uint4*>(sRoi + off512(r, col >> 3)) = pk;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  {
+    __half* o = out + static_cast<long>(b) * NBIN * D;
+    for (int id = tid; id < NBIN * 32; id += 256) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sRoi + off512(id >> 5, id & 31));
+      *reinterpret_cast<uint4*>(o + id * 8) = v;
+    }
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 RoiLevels make_levels(const void* const* feats, const int* hs, const int* ws, const float* scales) {
   RoiLevels lv;
   for (int i = 0; i < 3; ++i) {
@@ -548,6 +801,47 @@ int roi_dynconv_launch(const void* const* feats, const int* hs, const int* ws, c
         lv, boxes, boxes_per_frame, nullptr, static_cast<const __half*>(params), g1, b1, g2, b2,
         static_cast<__half*>(out));
   }
+  return check_launch();
+}
+
+
+// params: [M][32768] fp16 in the TRANSPOSED layout (P1^T [64][256] then P2^T [256][64] per box), see the kernel comment.
+int roi_dynconv_tc_launch(const void* const* feats, const int* hs, const int* ws, const float* scales,
+                          const float* boxes, int num_boxes, int boxes_per_frame, const void* roi_in,
+                          const void* params_t, const float* g1, const float* b1, const float* g2, const float* b2,
+                          void* out, cudaStream_t stream) {
+  if (num_boxes <= 0 || boxes_per_frame <= 0) return DVID_ERR_SHAPE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(roi_dynconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TOTAL) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(roi_dynconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_TOTAL) !=
+            cudaSuccess)
+      return DVID_ERR_CUDA;
+    attr_set = true;
+  }
+  DynMaps maps;
+  {
+    const uint64_t dims[3] = {256, 64, static_cast<uint64_t>(num_boxes)};
+    const uint64_t strides[2] = {512, 65536};
+    const uint32_t box[3] = {64, 64, 1};
+    int r = make_tmap_f16(&maps.p1, params_t, 3, dims, strides, box, nullptr);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[3] = {64, 256, static_cast<uint64_t>(num_boxes)};
+    const uint64_t strides[2] = {128, 65536};
+    const uint32_t box[3] = {64, 256, 1};
+    int r = make_tmap_f16(&maps.p2, static_cast<const __half*>(params_t) + D * DD, 3, dims, strides, box, nullptr);
+    if (r) return r;
+  }
+  const RoiLevels lv = make_levels(feats, hs, ws, scales);
+  if (roi_in != nullptr)
+    launch_pdl(roi_dynconv_tc_kernel<true>, dim3(num_boxes), dim3(256), TC_TOTAL, stream, maps, lv, boxes,
+               boxes_per_frame, static_cast<const __half*>(roi_in), g1, b1, g2, b2, static_cast<__half*>(out));
+  else
+    launch_pdl(roi_dynconv_tc_kernel<false>, dim3(num_boxes), dim3(256), TC_TOTAL, stream, maps, lv, boxes,
+               boxes_per_frame, static_cast<const __half*>(nullptr), g1, b1, g2, b2, static_cast<__half*>(out));
   return check_launch();
 }
 
