@@ -30,8 +30,10 @@ SIGNATURES = {
     "dvid_preprocess_u8": [P, P, I, I, I, I, I, I, P, P, P],
     "dvid_maxpool3x3s2_nhwc_f16": [P, P, I, I, I, I, P],
     "dvid_attention_hd32": [P, P, P, P, I, I, I, I, L, L, L, L, L, L, L, L, P],
+    "dvid_attention_hd32_tc": [P, P, P, P, I, I, I, I, L, L, L, L, L, L, L, L, P],
     "dvid_roi_align": [P, P, P, P, P, I, I, P, P, P, P],
     "dvid_roi_dynconv": [P, P, P, P, P, I, I, P, P, P, P, P, P, P, P],
+    "dvid_roi_dynconv_tc": [P, P, P, P, P, I, I, P, P, P, P, P, P, P, P],
     "dvid_row_post": [P, I, L, P, P, P, P, I, P, P, P, I, I, P, P, P, P, I, I, I, I, P, I, P],
     "dvid_small_linear": [P, P, P, P, I, I, I, I, I, P],
     "dvid_time_sinusoid": [P, P, P, I, P],

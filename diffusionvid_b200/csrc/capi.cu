@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 10
+#define DVID_ABI_VERSION 12
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -89,6 +89,14 @@ int dvid_attention_hd32(const void* q, const void* k, const void* v, void* o, in
                                 S(stream));
 }
 
+int dvid_attention_hd32_tc(const void* q, const void* k, const void* v, void* o, int batch, int heads, int lq, int lk,
+                           long q_rs, long k_rs, long v_rs, long o_rs, long q_bs, long k_bs, long v_bs, long o_bs,
+                           void* stream) {
+  if (!q || !k || !v || !o) return DVID_ERR_ARG;
+  return dvid::attention_tc_launch(q, k, v, o, batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs, q_bs, k_bs, v_bs, o_bs,
+                                   S(stream));
+}
+
 int dvid_roi_align(const void* const* feats, const int* hs, const int* ws, const float* scales, const float* boxes,
                    int num_boxes, int boxes_per_frame, void* roi_out, float* mean_f32, void* mean_f16, void* stream) {
   if (!feats || !hs || !ws || !scales || !boxes) return DVID_ERR_ARG;
@@ -112,6 +120,25 @@ int dvid_roi_dynconv(const void* const* feats, const int* hs, const int* ws, con
   }
   return dvid::roi_dynconv_launch(feats, hs, ws, scales, boxes, num_boxes, boxes_per_frame, roi_in, params, ln1_g,
                                   ln1_b, ln2_g, ln2_b, out, S(stream));
+}
+
+int dvid_roi_dynconv_tc(const void* const* feats, const int* hs, const int* ws, const float* scales, const float* boxes,
+                        int num_boxes, int boxes_per_frame, const void* roi_in, const void* params_t,
+                        const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, void* out,
+                        void* stream) {
+  if (!params_t || !ln1_g || !ln1_b || !ln2_g || !ln2_b || !out) return DVID_ERR_ARG;
+  if (!roi_in && (!feats || !hs || !ws || !scales || !boxes)) return DVID_ERR_ARG;
+  static const void* const null_feats[3] = {nullptr, nullptr, nullptr};
+  static const int zeros[3] = {0, 0, 0};
+  static const float zf[3] = {0.f, 0.f, 0.f};
+  if (roi_in) {
+    if (!feats) feats = null_feats;
+    if (!hs) hs = zeros;
+    if (!ws) ws = zeros;
+    if (!scales) scales = zf;
+  }
+  return dvid::roi_dynconv_tc_launch(feats, hs, ws, scales, boxes, num_boxes, boxes_per_frame, roi_in, params_t, ln1_g,
+                                     ln1_b, ln2_g, ln2_b, out, S(stream));
 }
 
 int dvid_row_post(const float* partials, int splits, long split_stride, const void* in_f16, const float* bias,

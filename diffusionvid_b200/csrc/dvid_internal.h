@@ -30,6 +30,10 @@ int attention_launch(const void* q, const void* k, const void* v, void* o, int b
                      long q_rs, long k_rs, long v_rs, long o_rs, long q_bs, long k_bs, long v_bs, long o_bs,
                      cudaStream_t stream);
 
+int attention_tc_launch(const void* q, const void* k, const void* v, void* o, int batch, int heads, int lq, int lk,
+                        long q_rs, long k_rs, long v_rs, long o_rs, long q_bs, long k_bs, long v_bs, long o_bs,
+                        cudaStream_t stream);
+
 int roi_align_launch(const void* const* feats, const int* hs, const int* ws, const float* scales, const float* boxes,
                      int num_boxes, int boxes_per_frame, void* roi_out, float* mean_f32, void* mean_f16,
                      cudaStream_t stream);
@@ -37,6 +41,11 @@ int roi_dynconv_launch(const void* const* feats, const int* hs, const int* ws, c
                        const float* boxes, int num_boxes, int boxes_per_frame, const void* roi_in, const void* params,
                        const float* g1, const float* b1, const float* g2, const float* b2, void* out,
                        cudaStream_t stream);
+
+int roi_dynconv_tc_launch(const void* const* feats, const int* hs, const int* ws, const float* scales,
+                          const float* boxes, int num_boxes, int boxes_per_frame, const void* roi_in,
+                          const void* params_t, const float* g1, const float* b1, const float* g2, const float* b2,
+                          void* out, cudaStream_t stream);
 
 int preprocess_launch(const void* img, int is_u8, void* out, int n, int H, int W, int halo, int Hp, int Wp,
                       const float* mean, const float* std, cudaStream_t stream);

@@ -130,6 +130,8 @@ class DiffusionDet(nn.Module):
         self.streamk = bool(int(__import__("os").environ.get("DVID_STREAMK", hp.get("streamk", 0))))
         self.fused_tail = bool(hp.get("fused_tail", True))
         import os as _os
+        # DynamicConv bmm pair on tcgen05 (roi_dynconv_tc_kernel) or on mma.sync (roi_dynconv_kernel, the round-1 kernel)
+        self.dynconv_tc = bool(int(_os.environ.get("DVID_DYNCONV_TC", hp.get("dynconv_tc", 1))))
         self.extract_batch = int(_os.environ.get("DVID_EXTRACT_BATCH", hp.get("extract_batch", 32)))
         self.dyn_chunk_frames = int(_os.environ.get("DVID_DYN_CHUNK", hp.get("dyn_chunk_frames", 0)))
         # frames that arrive in HOST memory: run the backbone on the frames already uploaded while the later ones are
@@ -222,6 +224,12 @@ class DiffusionDet(nn.Module):
             e["out_w"] = h16(pre + "self_attn.out_proj.weight"); e["out_b"] = sd[pre + "self_attn.out_proj.bias"]
             e["dyn_w"] = h16(pre + "inst_interact.dynamic_layer.weight")
             e["dyn_b"] = sd[pre + "inst_interact.dynamic_layer.bias"]
+            if self.dynconv_tc:
+                # the tcgen05 DynamicConv kernel takes the per-box weights transposed (K-major B operands): permute the
+                # rows of the Linear that generates them, once, here (ops.dynconv_permutation)
+                perm = ops.dynconv_permutation().to(dev)
+                e["dyn_w"] = e["dyn_w"][perm].contiguous()
+                e["dyn_b"] = e["dyn_b"][perm].contiguous()
             e["dn1"] = lnp(pre + "inst_interact.norm1"); e["dn2"] = lnp(pre + "inst_interact.norm2")
             e["dn3"] = lnp(pre + "inst_interact.norm3")
             e["ol_w"] = h16(pre + "inst_interact.out_layer.weight"); e["ol_b"] = sd[pre + "inst_interact.out_layer.bias"]
@@ -443,10 +451,11 @@ class DiffusionDet(nn.Module):
                 params = ops.gemm(p16[rows], e["dyn_w"], e["dyn_b"], out=pbuf[:(f1 - f0) * N])
                 sub = ops.Levels([f[f0:f1] for f in lv.feats])
                 ops.roi_dynconv(sub, boxes[f0:f1], N, params, e["dn1"][0], e["dn1"][1], e["dn2"][0], e["dn2"][1],
-                                roi_in=None if roi is None else roi[rows], out=f2[rows])
+                                roi_in=None if roi is None else roi[rows], out=f2[rows], transposed=self.dynconv_tc)
         else:
             params = ops.gemm(p16, e["dyn_w"], e["dyn_b"])
-            f2 = ops.roi_dynconv(lv, boxes, N, params, e["dn1"][0], e["dn1"][1], e["dn2"][0], e["dn2"][1], roi_in=roi)
+            f2 = ops.roi_dynconv(lv, boxes, N, params, e["dn1"][0], e["dn1"][1], e["dn2"][0], e["dn2"][1], roi_in=roi,
+                                 transposed=self.dynconv_tc)
         part, s = ops.gemm_partials(f2, e["ol_w"], 7)
         o32 = torch.empty((M, 256), device=dev, dtype=F32); o16 = torch.empty((M, 256), device=dev, dtype=H)
         ops.row_post(M, partials=part, splits=s, bias=e["ol_b"], ln1=e["dn3"], relu1=True, resid=p32, ln2=e["n2"],

@@ -180,14 +180,20 @@ def maxpool3x3s2(x):
 
 
 # ------------------------------------------------------------------------------------------------ decoder
-def attention(q, k, v, out, batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs, q_bs, k_bs, v_bs, o_bs):
-    """q/k/v/out: fp16 tensors (possibly views into a packed buffer); strides in elements."""
+ATTENTION_TC = bool(int(__import__("os").environ.get("DVID_ATTN_TC", "1")))
+
+
+def attention(q, k, v, out, batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs, q_bs, k_bs, v_bs, o_bs, tc=None):
+    """q/k/v/out: fp16 tensors (possibly views into a packed buffer); strides in elements.  tc: tcgen05 kernel
+    (dvid_attention_hd32_tc) or the mma.sync flash kernel (dvid_attention_hd32); None = module default ATTENTION_TC."""
+    tc = ATTENTION_TC if tc is None else tc
     for t, nme in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         if not t.is_cuda or t.dtype != H:
             raise _lib.DvidError(f"attention: {nme} must be CUDA fp16")
     with _prof("attention", 4.0 * batch * heads * lq * lk * 32, 2.0 * batch * heads * 32 * (2 * lq + 2 * lk)):
-        check(_lib.lib().dvid_attention_hd32(ptr(q), ptr(k), ptr(v), ptr(out), batch, heads, lq, lk, q_rs, k_rs, v_rs,
-                                             o_rs, q_bs, k_bs, v_bs, o_bs, cur_stream()), "dvid_attention_hd32")
+        fn = _lib.lib().dvid_attention_hd32_tc if tc else _lib.lib().dvid_attention_hd32
+        check(fn(ptr(q), ptr(k), ptr(v), ptr(out), batch, heads, lq, lk, q_rs, k_rs, v_rs,
+                 o_rs, q_bs, k_bs, v_bs, o_bs, cur_stream()), "dvid_attention_hd32_tc" if tc else "dvid_attention_hd32")
     _cnt()
     return out
 
@@ -220,7 +226,19 @@ def roi_align(levels, boxes, boxes_per_frame, want_roi=True, want_mean=True):
     return roi, mean32, mean16
 
 
-def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=None, out=None):
+def dynconv_permutation(d=256, dd=64):
+    """Row permutation of the dynamic_layer weight / bias that makes the GEMM emit the per-box weights in the layout
+    of dvid_roi_dynconv_tc: new row j*d+i <- old row i*dd+j (P1^T), new row d*dd+i*dd+j <- old row d*dd+j*d+i (P2^T)."""
+    i = torch.arange(d)[None, :]
+    j = torch.arange(dd)[:, None]
+    p1 = (i * dd + j).reshape(-1)                       # [j][i]
+    p2 = d * dd + (torch.arange(dd)[None, :] * d + torch.arange(d)[:, None]).reshape(-1)     # [i][j]
+    return torch.cat([p1, p2])
+
+
+def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=None, out=None, transposed=False):
+    """transposed=False: params in the reference's layout, mma.sync kernel (dvid_roi_dynconv); transposed=True: params
+    from a dynamic_layer whose rows were permuted with dynconv_permutation(), tcgen05 kernel (dvid_roi_dynconv_tc)."""
     _chk(boxes, F32, "boxes"); _chk(params, H, "params"); _chk(roi_in, H, "roi_in")
     for t in (g1, b1, g2, b2):
         _chk(t, F32, "ln")
@@ -230,10 +248,11 @@ def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=N
     lv = levels
     # algorithmic: two 49x256x64 bmm per box; bytes: generated weights in, 49x256 activations out (+ROI tile in)
     with _prof("roi_dynconv", 4.0 * m * 49 * 256 * 64, 2.0 * m * (32768 + 49 * 256 * 2)):
-        check(_lib.lib().dvid_roi_dynconv(lv.ptrs if lv else None, lv.hs if lv else None, lv.ws if lv else None,
-                                          lv.scales if lv else None, ptr(boxes), m, boxes_per_frame, ptr(roi_in),
-                                          ptr(params), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(out), cur_stream()),
-              "dvid_roi_dynconv")
+        fn = _lib.lib().dvid_roi_dynconv_tc if transposed else _lib.lib().dvid_roi_dynconv
+        check(fn(lv.ptrs if lv else None, lv.hs if lv else None, lv.ws if lv else None,
+                 lv.scales if lv else None, ptr(boxes), m, boxes_per_frame, ptr(roi_in),
+                 ptr(params), ptr(g1), ptr(b1), ptr(g2), ptr(b2), ptr(out), cur_stream()),
+              "dvid_roi_dynconv_tc" if transposed else "dvid_roi_dynconv")
     _cnt()
     return out
 

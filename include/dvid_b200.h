@@ -101,6 +101,12 @@ DVID_API int dvid_attention_hd32(const void* q, const void* k, const void* v, vo
                         long q_rs, long k_rs, long v_rs, long o_rs, long q_bs, long k_bs, long v_bs, long o_bs,
                         void* stream);
 
+/* The same contract with both contractions on tcgen05 (S and O accumulators in TMEM, softmax out of TMEM, 128 queries
+ * per CTA, keys in chunks of 128; csrc/attention_tc.cu).  All strides must be multiples of 8 elements. */
+DVID_API int dvid_attention_hd32_tc(const void* q, const void* k, const void* v, void* o, int batch, int heads, int lq,
+                           int lk, long q_rs, long k_rs, long v_rs, long o_rs, long q_bs, long k_bs, long v_bs,
+                           long o_bs, void* stream);
+
 /* detectron2 ROIPooler -> torchvision roi_align(aligned=True, 7x7, sampling_ratio 2) over 3 FPN levels (call sites
  * box_head.py:507,617).  feats: 3 host pointers to device NHWC fp16 maps [frames][h_l][w_l][256];
  * boxes [num_boxes][4] xyxy fp32, box b belongs to frame b / boxes_per_frame.  roi_out [num_boxes][49][256] fp16
@@ -116,6 +122,16 @@ DVID_API int dvid_roi_align(const void* const* feats, const int* hs, const int* 
 DVID_API int dvid_roi_dynconv(const void* const* feats, const int* hs, const int* ws, const float* scales, const float* boxes,
                      int num_boxes, int boxes_per_frame, const void* roi_in, const void* params, const float* ln1_g,
                      const float* ln1_b, const float* ln2_g, const float* ln2_b, void* out, void* stream);
+
+/* The same operation with both per-box contractions on tcgen05 (TMEM accumulators, LayerNorm out of TMEM, generated
+ * weights by TMA): params_t [num_boxes][32768] fp16 holds the dynamic_layer output TRANSPOSED per box - P1^T [64][256]
+ * (params_t[j*256+i] = P1[i][j]) then P2^T [256][64] (params_t[16384+i*64+j] = P2[j][i]) - i.e. the rows of the
+ * dynamic_layer weight / bias are permuted once when the weights are packed (box_head.py:693-696 fixes the layout of
+ * the reference's Linear; a row permutation of a Linear permutes its outputs and nothing else). */
+DVID_API int dvid_roi_dynconv_tc(const void* const* feats, const int* hs, const int* ws, const float* scales,
+                        const float* boxes, int num_boxes, int boxes_per_frame, const void* roi_in,
+                        const void* params_t, const float* ln1_g, const float* ln1_b, const float* ln2_g,
+                        const float* ln2_b, void* out, void* stream);
 
 /* Row kernel for 256-wide rows: y = sum_s partials[s] (or in_f16) + bias -> [LN1] -> [ReLU] -> [+resid] -> [LN2] ->
  * act2 (0 none / 1 ReLU / 2 SiLU; on the fp16 output only if act2_f16_only) -> out_f32 / out_f16; optional time /

@@ -78,7 +78,7 @@ def maxpool3x3s2(x):
     return F.max_pool2d(_nhwc_to_nchw(x), 3, 2, 1).permute(0, 2, 3, 1).contiguous().half()
 
 
-def attention(q, k, v, out, batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs, q_bs, k_bs, v_bs, o_bs):
+def attention(q, k, v, out, batch, heads, lq, lk, q_rs, k_rs, v_rs, o_rs, q_bs, k_bs, v_bs, o_bs, tc=None):
     def view(t, L, rs, bs):
         base = t.reshape(-1) if t.is_contiguous() else None
         rows = []
@@ -110,12 +110,24 @@ def roi_align(levels, boxes, boxes_per_frame, want_roi=True, want_mean=True):
     return (roi if want_roi else None), (mean if want_mean else None), (mean.half() if want_mean else None)
 
 
-def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=None, out=None):
+def dynconv_permutation(d=256, dd=64):
+    i = torch.arange(d)[None, :]
+    j = torch.arange(dd)[:, None]
+    p1 = (i * dd + j).reshape(-1)
+    p2 = d * dd + (torch.arange(dd)[None, :] * d + torch.arange(d)[:, None]).reshape(-1)
+    return torch.cat([p1, p2])
+
+
+def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=None, out=None, transposed=False):
     if roi_in is None:
         roi_in, _, _ = roi_align(levels, boxes, boxes_per_frame, True, False)
     M = params.shape[0]
-    p1 = params[:, :16384].float().view(M, 256, 64)
-    p2 = params[:, 16384:].float().view(M, 64, 256)
+    if transposed:
+        p1 = params[:, :16384].float().view(M, 64, 256).transpose(1, 2)
+        p2 = params[:, 16384:].float().view(M, 256, 64).transpose(1, 2)
+    else:
+        p1 = params[:, :16384].float().view(M, 256, 64)
+        p2 = params[:, 16384:].float().view(M, 64, 256)
     f = F.relu(F.layer_norm(torch.bmm(roi_in.float(), p1), (64,), g1, b1)).half().float()
     f = F.relu(F.layer_norm(torch.bmm(f, p2), (256,), g2, b2)).half().reshape(M, 49 * 256)
     if out is not None:

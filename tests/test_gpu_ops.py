@@ -20,9 +20,11 @@ def gen(seed):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("batch,lq,lk", [(2, 300, 300), (8, 300, 300), (1, 64, 64), (3, 100, 37)])
-def test_self_attention_packed_qkv(cuda, batch, lq, lk):
-    """self-attention layout: packed [batch*N, 768] qkv buffer read in place (box_head.py:515-516)."""
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("batch,lq,lk", [(2, 300, 300), (8, 300, 300), (1, 64, 64), (3, 100, 37), (2, 129, 257)])
+def test_self_attention_packed_qkv(cuda, batch, lq, lk, tc):
+    """self-attention layout: packed [batch*N, 768] qkv buffer read in place (box_head.py:515-516); tc selects the
+    tcgen05 kernel (dvid_attention_hd32_tc) or the mma.sync one (dvid_attention_hd32)."""
     assert lq == lk or True
     g = gen(batch * 1000 + lq)
     n = max(lq, lk)
@@ -30,7 +32,7 @@ def test_self_attention_packed_qkv(cuda, batch, lq, lk):
     out = torch.zeros(batch * n, 256, dtype=torch.float16, device=cuda)
     d = qkv.to(cuda)
     ops.attention(d, d[:, 256:], d[:, 512:], out, batch, 8, lq, lk, 768, 768, 768, 256, n * 768, n * 768, n * 768,
-                  n * 256)
+                  n * 256, tc=tc)
     x = qkv.float().view(batch, n, 3, 8, 32)
     q, k, v = x[:, :lq, 0], x[:, :lk, 1], x[:, :lk, 2]
     att = torch.softmax(torch.einsum("blhd,bshd->bhls", q, k) / math.sqrt(32), dim=-1)
@@ -39,14 +41,15 @@ def test_self_attention_packed_qkv(cuda, batch, lq, lk):
     assert (got - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())
 
 
-def test_cross_attention(cuda):
+@pytest.mark.parametrize("tc", [False, True])
+def test_cross_attention(cuda, tc):
     """global attention layout (box_head.py:366-371): 2400 queries, 900 memory keys, batch 1."""
     g = gen(5)
     q = torch.randn(2400, 256, generator=g).half()
     kv = torch.randn(900, 512, generator=g).half()
     out = torch.zeros(2400, 256, dtype=torch.float16, device=cuda)
     qd, kvd = q.to(cuda), kv.to(cuda)
-    ops.attention(qd, kvd, kvd[:, 256:], out, 1, 8, 2400, 900, 256, 512, 512, 256, 0, 0, 0, 0)
+    ops.attention(qd, kvd, kvd[:, 256:], out, 1, 8, 2400, 900, 256, 512, 512, 256, 0, 0, 0, 0, tc=tc)
     qq = q.float().view(2400, 8, 32)
     kk = kv.float()[:, :256].reshape(900, 8, 32)
     vv = kv.float()[:, 256:].reshape(900, 8, 32)
@@ -100,8 +103,11 @@ def _dynconv_ref(roi, params, g1, b1, g2, b2):
     return F.relu(F.layer_norm(f, (256,), g2, b2))
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("fused", [False, True])
-def test_roi_dynconv(cuda, fused):
+def test_roi_dynconv(cuda, fused, tc):
+    """tc=False: mma.sync kernel, params in the reference's layout; tc=True: tcgen05 kernel (dvid_roi_dynconv_tc), params
+    as the row-permuted dynamic_layer emits them (ops.dynconv_permutation)."""
     g = gen(13)
     frames, n = 2, 150
     M = frames * n
@@ -114,8 +120,12 @@ def test_roi_dynconv(cuda, fused):
     roi_ref = oo.roi_pooler([f.float() for f in nchw], boxes).view(M, 256, 49).permute(0, 2, 1).half()
     ref = _dynconv_ref(roi_ref, params, g1, b1, g2, b2)
     roi_in = None if fused else roi_ref.contiguous().to(cuda)
-    out = ops.roi_dynconv(lv, boxes.to(cuda), n, params.to(cuda), g1.to(cuda), b1.to(cuda), g2.to(cuda), b2.to(cuda),
-                          roi_in=roi_in)
+    pk = params[:, ops.dynconv_permutation()].contiguous() if tc else params
+    if tc:      # the permutation is the transposition the kernel documents
+        assert torch.equal(pk[:, :16384].view(M, 64, 256), params[:, :16384].view(M, 256, 64).transpose(1, 2))
+        assert torch.equal(pk[:, 16384:].view(M, 256, 64), params[:, 16384:].view(M, 64, 256).transpose(1, 2))
+    out = ops.roi_dynconv(lv, boxes.to(cuda), n, pk.to(cuda), g1.to(cuda), b1.to(cuda), g2.to(cuda), b2.to(cuda),
+                          roi_in=roi_in, transposed=tc)
     got = out.float().cpu().view(M, 49, 256)
     err = (got - ref).abs().max().item()
     # two LayerNorms amplify fp16 rounding of the intermediates; 1.5e-2 abs on O(1..4) outputs
