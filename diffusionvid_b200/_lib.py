@@ -55,6 +55,7 @@ SIGNATURES = {
     "dvid_resize_workspace_bytes": [I, I, I, I, I],
     "dvid_resize_bilinear_u8": [P, I, I, I, I, I, P, I, I, P, L, P],
     "dvid_swin_window_attention": [P, P, P, I, I, I, I, I, I, P],
+    "dvid_swin_window_attention_tc": [P, P, P, I, I, I, I, I, I, P],
 }
 
 

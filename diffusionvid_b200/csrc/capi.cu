@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 12
+#define DVID_ABI_VERSION 13
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -268,6 +268,12 @@ int dvid_swin_window_attention(const void* qkv, const float* bias, void* out_f16
                                int heads, int shift, void* stream) {
   if (!qkv || !bias || !out_f16) return DVID_ERR_ARG;
   return dvid::swin_window_attention_launch(qkv, bias, out_f16, B, H, W, C, heads, shift, S(stream));
+}
+
+int dvid_swin_window_attention_tc(const void* qkv, const float* bias, void* out_f16, int B, int H, int W, int C,
+                                  int heads, int shift, void* stream) {
+  if (!qkv || !bias || !out_f16) return DVID_ERR_ARG;
+  return dvid::swin_window_attention_tc_launch(qkv, bias, out_f16, B, H, W, C, heads, shift, S(stream));
 }
 
 }  // extern "C"

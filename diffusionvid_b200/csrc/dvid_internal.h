@@ -101,6 +101,9 @@ int swin_patch_gather_launch(const void* img, int is_u8, void* out, int B, int H
 int swin_window_attention_launch(const void* qkv, const float* bias, void* out, int B, int H, int W, int C, int heads,
                                  int shift, cudaStream_t stream);
 
+int swin_window_attention_tc_launch(const void* qkv, const float* bias, void* out, int B, int H, int W, int C, int heads,
+                                    int shift, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------------------------
 // Programmatic dependent launch: every kernel of the library is launched with the programmatic-stream-serialization
 // attribute and starts with pdl_prologue(): `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be

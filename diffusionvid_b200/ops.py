@@ -450,13 +450,22 @@ def swin_patch_gather(img, mean, std):
     return out
 
 
-def swin_window_attention(qkv, bias, B, Hh, W, C, heads, shift):
+# default: the mma.sync kernel - one 49x49x32 window per CTA finishes in registers; the tcgen05 variant (two windows per
+# 128-row tile, TMEM round trips, per-CTA TMEM allocation) measured 2.5-3.3x slower at the Swin-B shapes
+# (profiles/r02_attention_ab.json), so it is the opt-in
+SWIN_ATTENTION_TC = bool(int(__import__("os").environ.get("DVID_SWIN_ATTN_TC", "0")))
+
+
+def swin_window_attention(qkv, bias, B, Hh, W, C, heads, shift, tc=None):
+    """tc: tcgen05 kernel (dvid_swin_window_attention_tc) or the mma.sync one; None = module default."""
+    tc = SWIN_ATTENTION_TC if tc is None else tc
     _chk(qkv, H, "qkv"); _chk(bias, F32, "bias")
     out = torch.empty((qkv.shape[0], C), device=qkv.device, dtype=H)
     nw = B * ((Hh + 6) // 7) * ((W + 6) // 7)
     with _prof("attention", 4.0 * nw * heads * 49 * 49 * 32, 2.0 * qkv.numel() + 2.0 * out.numel()):
-        check(_lib.lib().dvid_swin_window_attention(ptr(qkv), ptr(bias), ptr(out), B, Hh, W, C, heads, shift,
-                                                    cur_stream()), "dvid_swin_window_attention")
+        fn = _lib.lib().dvid_swin_window_attention_tc if tc else _lib.lib().dvid_swin_window_attention
+        check(fn(ptr(qkv), ptr(bias), ptr(out), B, Hh, W, C, heads, shift, cur_stream()),
+              "dvid_swin_window_attention")
     _cnt()
     return out
 

@@ -258,6 +258,10 @@ DVID_API int dvid_swin_patch_gather_u8(const unsigned char* img, void* out_f16, 
  * the token coordinates.  H, W: token grid of the stage (unpadded). */
 DVID_API int dvid_swin_window_attention(const void* qkv, const float* bias, void* out_f16, int B, int H, int W, int C,
                                int heads, int shift, void* stream);
+/* The same contract on tcgen05: two windows (2 x 64 padded rows) per 128-row tile, scores and outputs in TMEM, bias +
+ * shift mask + softmax out of TMEM (csrc/swin_attention_tc.cu). */
+DVID_API int dvid_swin_window_attention_tc(const void* qkv, const float* bias, void* out_f16, int B, int H, int W, int C,
+                                  int heads, int shift, void* stream);
 
 #ifdef __cplusplus
 }

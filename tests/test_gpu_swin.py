@@ -60,15 +60,17 @@ def test_swin_rows_modes(cuda):
     assert (m.float().cpu() - F.layer_norm(cat, (512,), g4, b4, 1e-5)).abs().max().item() <= 4e-3
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("shift", [0, 3])
-def test_window_attention_matches_reference_math(cuda, shift):
+@pytest.mark.parametrize("B", [2, 1, 3])        # 12, 6 and 18 windows; with B = 3 x (1 x 3) windows below: odd count
+def test_window_attention_matches_reference_math(cuda, shift, tc, B):
     g = torch.Generator().manual_seed(1)
-    B, Hh, W, C, nh = 2, 10, 16, 128, 4
-    nwy, nwx = 2, 3
+    Hh, W, C, nh = (10, 16, 128, 4) if B != 3 else (7, 16, 128, 4)
+    nwy, nwx = (Hh + 6) // 7, (W + 6) // 7
     rows = B * nwy * nwx * 49
     qkv = (0.7 * torch.randn(rows, 3 * C, generator=g)).half()
     bias = 0.5 * torch.randn(nh, 49, 49, generator=g)
-    out = ops.swin_window_attention(qkv.to(cuda), bias.to(cuda), B, Hh, W, C, nh, shift)
+    out = ops.swin_window_attention(qkv.to(cuda), bias.to(cuda), B, Hh, W, C, nh, shift, tc=tc)
     q, k, v = qkv.float().view(-1, 49, 3, nh, 32).permute(2, 0, 3, 1, 4)
     att = (q * 32 ** -0.5) @ k.transpose(-2, -1) + bias[None]
     if shift:
