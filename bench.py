@@ -567,6 +567,19 @@ def run_ours(args):
                     "hbm": {"algorithmic_bytes_per_head_eval": 82e6, "achieved_gbs": 82e6 * evals / dms / 1e6,
                             "peak_gbs": peak_bw, "frac": 82e6 * evals / dms / 1e6 / peak_bw},
                     "roi_dynconv_kernel": roof.pop("decoder_step", None)}
+            # whole-step algorithmic work: backbone GFLOP per frame (R-101+FPN 213.08 hook-counted,
+            # Swin-B+FPN 423.4 analytic incl. window padding) on every local + global frame, 3 base head evaluations per
+            # frame at extraction, T x (3 + 1) head evaluations + T global attentions per local frame in the DDIM loop
+            bb_gf = 423.4 if args.backbone == "swinb" else 213.08
+            he_gf = 72.6 / 8.0 * args.proposals / 300.0
+            nfr = args.frames + args.global_frames
+            dec_evals = (args.T * 4 if args.T > 1 else 1)
+            step_gf = nfr * (bb_gf + 3 * he_gf) + args.frames * (dec_evals * he_gf + args.T * 3.1 / 8.0)
+            roof["step"] = {"algorithmic_tflop_per_step": step_gf / 1e3, "achieved": step_gf / clip_ms,
+                            "peak": peak_tf, "unit": "TFLOP/s", "frac": step_gf / clip_ms / peak_tf,
+                            "backbone": "Swin-B+FPN 423.4 GFLOP/frame" if args.backbone == "swinb"
+                            else "R-101+FPN 213.08 GFLOP/frame",
+                            "backbone_share_of_flops": nfr * bb_gf / step_gf}
             ext = units.get(("extract", hp["infer_batch"])) or units.get(("features", hp["infer_batch"]))
             if ext:
                 roof["extract_unit_ms"] = statistics.median(ext)
