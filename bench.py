@@ -30,8 +30,10 @@ reference frames at the video start (backbone + 3 base stages on all 88 frames, 
 
 N>1 (torchrun): video-level sharding as in the reference (VIDTestDistributedSampler): every rank processes its own
 clips, no data-path collective; value = total frames of all ranks / max-over-ranks time ("weak" scaling).  The line
-additionally carries `frame_sharded`: ONE clip dealt frame by frame to the N ranks (BASELINE config 5; strong scaling,
-one all-gather of memory candidates per video + one all-gather of detections per key batch).
+additionally carries BASELINE config 5 - ONE clip spread over the N ranks (strong scaling), in both granularities of
+DiffusionDet.set_frame_sharding: `frame_sharded` (frame i of every call on rank i % N: one all-gather of memory
+candidates per video + one all-gather of detections per key batch, every rank returns the whole clip) and
+`batch_sharded` (key batch k on rank k % N, the global frames dealt frame by frame: the memory all-gather only).
 """
 import argparse
 import json
@@ -480,7 +482,7 @@ def run_ours(args):
         m.host_results = False
 
         # N > 1: the SAME clip dealt frame by frame to the ranks (BASELINE config 5)
-        fs = None
+        fs = bs = None
         if dist and not shard_frames and not args.no_frame_sharded:
             m.set_frame_sharding(rank, world)
             for _ in range(2):
@@ -495,6 +497,20 @@ def run_ours(args):
                   "results_allgather_bytes_per_step": (m.comm_bytes["results"] - cb0["results"]) // max(1, args.steps),
                   "collectives_per_step": "1 all-gather of memory candidates per video + 1 all-gather of detections "
                                           "per key batch (NCCL)"}
+            # the same clip sharded by whole key batches: batch k on rank k % world, no per-batch exchange
+            m.set_frame_sharding(rank, world, mode="batches")
+            for _ in range(2):
+                run_clip(m, dev_samples, False)
+            cb0 = dict(m.comm_bytes)
+            ms_bs, frames_bs, _, _ = timed(m, dev_samples, args.steps, False, dist, dev)
+            tot = torch.tensor([frames_bs], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(tot)
+            bs = {"value": float(tot.item()) / (ms_bs / 1000.0), "unit": "frames/s", "scaling": "strong",
+                  "ms_per_step": ms_bs / args.steps, "frames_per_step_all_ranks": float(tot.item()) / args.steps,
+                  "memory_allgather_bytes_per_video": (m.comm_bytes["memory"] - cb0["memory"]) // max(1, args.steps),
+                  "collectives_per_step": "1 all-gather of memory candidates per video (NCCL); every rank returns the "
+                                          "BoxLists of its own key batches, merged at the end like "
+                                          "engine/inference.py:96-116"}
             m.set_frame_sharding(rank, 1)
 
         # device time of the captured execution units in a normal (graph-replayed) pass of the clip
@@ -596,9 +612,10 @@ def run_ours(args):
     e2e_value = frames_e2e * mult / (ms_e2e / 1000.0)
     e2e_u8_value = frames_u8 * mult / (ms_u8 / 1000.0)
     e2e_eng_value = frames_eng * mult / (ms_eng / 1000.0)
-    if fs is not None:
-        fs["efficiency_vs_video_sharded"] = fs["value"] / value       # value = N x the un-sharded per-GPU rate
-        fs["speedup_vs_one_gpu"] = fs["value"] / (value / world)
+    for rec in (fs, bs):
+        if rec is not None:
+            rec["efficiency_vs_video_sharded"] = rec["value"] / value       # value = N x the un-sharded per-GPU rate
+            rec["speedup_vs_one_gpu"] = rec["value"] / (value / world)
     if rank != 0:
         if dist:
             torch.distributed.destroy_process_group()
@@ -638,7 +655,7 @@ def run_ours(args):
                                    "per call (:35-40; cur is a second upload of a frame that also arrives as a ref), "
                                    "model(images), torch.cuda.synchronize() per call (:70-73), outputs .to(cpu) (:75)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
-            "frame_sharded": fs}
+            "frame_sharded": fs, "batch_sharded": bs}
     print(json.dumps(line))
     if dist:
         torch.distributed.destroy_process_group()

@@ -160,6 +160,7 @@ class DiffusionDet(nn.Module):
         self.deferred_results = bool(int(_os.environ.get("DVID_DEFERRED_RESULTS", hp.get("deferred_results", 1))))
         self.host_results = bool(hp.get("host_results", False))
         self._shard = None
+        self._shard_mode = "frames"
         self.eval()
 
     # ------------------------------------------------------------------------------------------ weight packing
@@ -770,7 +771,10 @@ class DiffusionDet(nn.Module):
             # start the host->device copy of the queued frame now, on the copy stream, so that it overlaps the compute
             # of the current key batch instead of serialising in front of the next one (this rank's frames only)
             for il in ref_l:
-                own = len(self.local_img_queue) % world == rank
+                if world > 1 and self._shard_mode == "batches":     # the queued frames form the NEXT key batch
+                    own = ((fid - infos.get("start_id", 0)) // ib + 1) % world == rank
+                else:
+                    own = len(self.local_img_queue) % world == rank
                 self.local_img_queue.append(self._upload(il, dev) if own else il)
             q = self.local_img_queue
             if (self.pipeline_uploads and self.pipeline_chunk > 0 and world == 1 and self._early is None
@@ -792,8 +796,10 @@ class DiffusionDet(nn.Module):
         if ref_l or ref_g:
             all_imgs = ref_l + ref_g
             n_total, len_l = len(all_imgs), len(ref_l)
-            # frame sharding (SURVEY.md 8e mode B): frame i of this call belongs to rank i % world
-            mine = [i for i in range(n_total) if i % world == rank]
+            # sharding of one clip (SURVEY.md 8e mode B): see set_frame_sharding for the two ownership rules
+            kb_index = (fid - infos.get("start_id", 0)) // ib
+            owner = [self._frame_owner(i, len_l, kb_index, world) for i in range(n_total)]
+            mine = [i for i in range(n_total) if owner[i] == rank]
             pos = {g: j for j, g in enumerate(mine)}
             ex = None
             early, self._early = self._early, None
@@ -831,7 +837,7 @@ class DiffusionDet(nn.Module):
                     outs.append({k: v.clone() for k, v in o.items()} if self._graph_active() else o)
                 ex = {k: (torch.cat([o[k] for o in outs]) if len(outs) > 1 else outs[0][k]) for k in outs[0]}
             if ref_g and hp["global_enable"]:
-                g1, g2 = self._gather_global_candidates(ex, pos, len_l, n_total, dev)
+                g1, g2 = self._gather_global_candidates(ex, pos, len_l, n_total, dev, owner)
                 self._set_memory([self._update_memory(g1, self.proposal_feats_global[0], hp["mem_size"]),
                                   self._update_memory(g2, self.proposal_feats_global[1], hp["mem_size2"])])
             if infos["frame_category"] == 0:
@@ -878,7 +884,10 @@ class DiffusionDet(nn.Module):
                 r = self._decode(**tensors, **consts, trace=self.last_trace, fid=fid)
             else:
                 r = self._run_unit("decode", self._decode, (w, h), tensors, consts)
-        if world > 1:
+        if world > 1 and self._shard_mode == "batches":
+            if r is None:
+                return []          # another rank's key batch: its owner returns (and later contributes) the results
+        elif world > 1:
             r = self._exchange_results(r, own, batch, cap, dev)
         if self.host_results and dev.type == "cuda":
             return self._results_on_host(r, batch, cap, w, h)
@@ -993,14 +1002,38 @@ class DiffusionDet(nn.Module):
         return results
 
     # ------------------------------------------------------------------------------------------ frame sharding
-    def set_frame_sharding(self, rank, world, group=None):
-        """SURVEY.md 8e mode B: the frames of every clip are dealt round-robin to the `world` ranks of `group`
-        (torch.distributed; NCCL on GPUs).  Every rank must be fed the same sample stream; per video one all-gather
-        moves the top-75/top-25 memory candidates of the global frames, per key batch one all-reduce assembles the
-        detections, so every rank returns the full result list.  world == 1 disables sharding."""
-        self._shard = (int(rank), int(world), group) if world > 1 else None
+    def set_frame_sharding(self, rank, world, group=None, mode="frames"):
+        """SURVEY.md 8e mode B / BASELINE config 5: ONE clip spread over the `world` ranks of `group`
+        (torch.distributed; NCCL on GPUs).  Every rank is fed the same sample stream.  Per video one all-gather moves
+        the top-75/top-25 memory candidates of the global frames (the only cross-frame dependency: every rank then runs
+        the deterministic farthest-point sampling redundantly).  Two granularities:
 
-    def _gather_global_candidates(self, ex, pos, len_l, n_total, dev):
+          mode="frames"   frame i of every call belongs to rank i % world (B_local = 8 / world frames of each key
+                          batch); one all-gather of detections per key batch, so EVERY rank returns the full list.
+          mode="batches"  whole key batches: batch k of the video belongs to rank k % world, which runs it exactly
+                          as a single GPU would (8 frames, full tiles); the global frames of the video start are dealt
+                          frame by frame.  A rank returns the BoxLists of ITS batches and [] for the others - the
+                          reference's own multi-GPU contract (every rank contributes what it computed, predictions are
+                          merged at the end, engine/inference.py:96-116) - so no per-batch exchange and no waiting.
+
+        Either way the detections are bit-identical to the single-process run (the kernels are batch-invariant).
+        world == 1 disables sharding."""
+        if mode not in ("frames", "batches"):
+            raise ValueError("mode must be 'frames' or 'batches'")
+        self._shard = (int(rank), int(world), group) if world > 1 else None
+        self._shard_mode = mode
+
+    def _frame_owner(self, i, len_l, key_batch, world):
+        """Rank that owns frame i of a key call's [local..., global...] list."""
+        if world == 1:
+            return 0
+        if self._shard_mode == "frames":
+            return i % world
+        if i < len_l:
+            return key_batch % world
+        return (i - len_l + 1) % world       # global frames: start behind the owner of batch 0, which has 8 local frames
+
+    def _gather_global_candidates(self, ex, pos, len_l, n_total, dev, owner=None):
         """(G*75,256) / (G*25,256) memory candidates of the global frames in frame order (diffusion_det.py:476-488)."""
         hp = self.hp
         N = self.num_proposals
@@ -1010,9 +1043,11 @@ class DiffusionDet(nn.Module):
         import torch.distributed as dist
         rank, world, group = self._shard
         gl = list(range(len_l, n_total))
-        per = max(1, max(sum(1 for i in gl if i % world == r) for r in range(world)))
+        if owner is None:
+            owner = [i % world for i in range(n_total)]
+        per = max(1, max(sum(1 for i in gl if owner[i] == r) for r in range(world)))
         send = torch.zeros((per, k1 + k2, 256), device=dev, dtype=F32)
-        for j, i in enumerate([i for i in gl if i % world == rank]):
+        for j, i in enumerate([i for i in gl if owner[i] == rank]):
             send[j, :k1] = ex["k1"][pos[i]]
             send[j, k1:] = ex["k2"][pos[i]]
         recv = torch.empty((world,) + tuple(send.shape), device=dev, dtype=F32)
@@ -1028,7 +1063,7 @@ class DiffusionDet(nn.Module):
         seen = [0] * world
         rows = []
         for i in gl:
-            r = i % world
+            r = owner[i]
             rows.append(recv[r][seen[r]])
             seen[r] += 1
         allc = torch.stack(rows)

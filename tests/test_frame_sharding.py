@@ -20,16 +20,16 @@ H, W, L = 64, 96, 11
 GIDX = [9, 2, 5]
 
 
-def _run(rank, world, T, port, out_dir):
+def _run(rank, world, T, port, out_dir, mode="frames"):
     real_ops, real_threads = pm.ops, torch.get_num_threads()
     try:
-        _run_impl(rank, world, T, port, out_dir)
+        _run_impl(rank, world, T, port, out_dir, mode)
     finally:            # the world == 1 run happens inside the pytest process: do not leak the shim to other tests
         pm.ops = real_ops
         torch.set_num_threads(real_threads)
 
 
-def _run_impl(rank, world, T, port, out_dir):
+def _run_impl(rank, world, T, port, out_dir, mode="frames"):
     torch.set_num_threads(1)       # same CPU kernels in every process: results must not depend on the world size
     pm.ops = cpu_ops_shim
     hp = dict(SMALL, sample_step=T)
@@ -38,9 +38,10 @@ def _run_impl(rank, world, T, port, out_dir):
     m.noise = om.NoiseSource(3, hp["num_proposals"])
     if world > 1:
         dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
-        m.set_frame_sharding(rank, world)
+        m.set_frame_sharding(rank, world, mode=mode)
     frames = synth.make_clip(L, H, W, seed=5)
     res = []
+    own_frames = []
     for s in synth.clip_samples(frames, GIDX, H, W):
         out = m(dict(cur=structures.ImageList(s["cur"], [(H, W)]),
                      ref_l=[structures.ImageList(t, [(H, W)]) for t in s["ref_l"]],
@@ -48,7 +49,9 @@ def _run_impl(rank, world, T, port, out_dir):
                      frame_id=s["frame_id"], start_id=0, end_id=L - 1, seg_len=L, frame_category=s["frame_category"],
                      video_id=0))
         res += [(b.bbox.clone(), b.get_field("scores").clone(), b.get_field("labels").clone()) for b in out]
-    torch.save(dict(res=res, mem=m.proposal_feats_global[0]), os.path.join(out_dir, "r%d_w%d.pt" % (rank, world)))
+        own_frames += [s["frame_id"] + i for i in range(len(out))]
+    torch.save(dict(res=res, frames=own_frames, mem=m.proposal_feats_global[0]),
+               os.path.join(out_dir, "r%d_w%d.pt" % (rank, world)))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -79,3 +82,20 @@ def test_two_rank_frame_sharding_matches_single_process(tmp_path, T):
     b = torch.load(os.path.join(tmp_path, "r1_w2.pt"))["res"]
     for x, y in zip(a, b):        # both ranks hold the identical all-reduced result
         assert all(torch.equal(p, q) for p, q in zip(x, y))
+
+
+def test_two_rank_key_batch_sharding_matches_single_process(tmp_path):
+    """mode="batches": key batch k of the clip belongs to rank k % 2 and is returned by that rank only; together the two
+    ranks hold the single-process detections (L = 11: batch 0 = frames 0..7 on rank 0, batch 1 = frames 8..10 on rank 1);
+    the replicated global memory equals the single-process one."""
+    T = 4
+    _run(0, 1, T, 0, str(tmp_path))
+    mp.spawn(_run, args=(2, T, _free_port(), str(tmp_path), "batches"), nprocs=2, join=True)
+    ref = torch.load(os.path.join(tmp_path, "r0_w1.pt"))
+    got = [torch.load(os.path.join(tmp_path, "r%d_w2.pt" % r)) for r in (0, 1)]
+    assert got[0]["frames"] == list(range(8)) and got[1]["frames"] == list(range(8, L))
+    for g in got:
+        assert (g["mem"] - ref["mem"]).abs().max().item() <= 1e-4
+        fr = [match_fraction(gb, gs, gl, *ref["res"][f], max(H, W), box_tol=1e-3, score_tol=1e-3)
+              for f, (gb, gs, gl) in zip(g["frames"], g["res"])]
+        assert min(fr) >= 0.9 and sum(fr) / len(fr) >= 0.97, fr
