@@ -161,6 +161,11 @@ class DiffusionDet(nn.Module):
         self.host_results = bool(hp.get("host_results", False))
         self._shard = None
         self._shard_mode = "frames"
+        # The DDIM decode of key batch k and the backbone / base stages of batch k+1 do not depend on each other: run the
+        # decode unit on its own stream, so that the (latency-bound, small-grid) decoder kernels of batch k share the GPU
+        # with the dense convolutions of batch k+1 instead of queueing in front of them.
+        self.overlap_decode = bool(int(_os.environ.get("DVID_OVERLAP_DECODE", hp.get("overlap_decode", 1))))
+        self._decode_stream = None
         self.eval()
 
     # ------------------------------------------------------------------------------------------ weight packing
@@ -543,6 +548,12 @@ class DiffusionDet(nn.Module):
         ops.furthest_point_sampling(1, n, target, dist, temp, idx)
         return merged[idx[0].long()]
 
+    def _for_decode(self, t):
+        """Tensors produced on the caller's stream and read by the decode stream: tell the caching allocator."""
+        if self._decode_stream is not None and t is not None and t.is_cuda:
+            t.record_stream(self._decode_stream)
+        return t
+
     def _set_memory(self, mem):
         self.proposal_feats_global = mem
         if mem[0] is not None and "ga" in self._pk:
@@ -550,7 +561,7 @@ class DiffusionDet(nn.Module):
             m16 = torch.empty(mem[0].shape, device=mem[0].device, dtype=H)
             # fp32 -> fp16 cast through the row kernel, then K/V projection once per video (the memory is constant)
             ops.row_post(mem[0].shape[0], partials=mem[0].contiguous(), splits=1, out_f16=m16)
-            self._mem_kv = ops.gemm(m16, ga["kv_w"], ga["kv_b"])
+            self._mem_kv = self._for_decode(ops.gemm(m16, ga["kv_w"], ga["kv_b"]))
 
     # ------------------------------------------------------------------------------------------ noise
     def _randn(self, kind, key_frame, index, frames, dev):
@@ -755,6 +766,8 @@ class DiffusionDet(nn.Module):
         dev = torch.device(self.device)
         if dev.type == "cuda":
             ops.conv_streamk(self.streamk)       # process-wide library switch: set per call (several models may coexist)
+            if self.overlap_decode and self._decode_stream is None:
+                self._decode_stream = torch.cuda.Stream()
         N = self.num_proposals
         ib = self.infer_batch
         if infos["frame_category"] == 0:
@@ -850,13 +863,29 @@ class DiffusionDet(nn.Module):
             for i in fill:
                 if i in pos:
                     j = pos[i]
-                    self.feats.append([ex[l][j:j + 1] for l in ("p3", "p4", "p5")])
-                    self.cache.append((ex["lg"][j:j + 1], ex["bx"][j:j + 1], ex["o32"][j:j + 1], ex["o16"][j:j + 1]))
+                    self.feats.append([self._for_decode(ex[l][j:j + 1]) for l in ("p3", "p4", "p5")])
+                    self.cache.append(tuple(self._for_decode(ex[l][j:j + 1]) for l in ("lg", "bx", "o32", "o16")))
                 else:       # another rank owns this frame
                     self.feats.append(None)
                     self.cache.append(None)
 
-        # 2. the key batch (this rank's frames of it)
+        # 2. the key batch (this rank's frames of it), on the decode stream when the overlap is on
+        overlap = (self.overlap_decode and dev.type == "cuda" and not self.debug_trace
+                   and (world == 1 or self._shard_mode == "batches"))
+        if not overlap:
+            return self._key_batch(infos, fid, w, h, dev, rank, world, None)
+        ev = torch.cuda.Event()
+        ev.record()                                   # everything the decode reads has been enqueued before this point
+        self._decode_stream.wait_event(ev)
+        with torch.cuda.stream(self._decode_stream):
+            return self._key_batch(infos, fid, w, h, dev, rank, world, self._decode_stream)
+
+    def _key_batch(self, infos, fid, w, h, dev, rank, world, stream):
+        """DDIM decode + post-processing + result hand-over of one key batch (diffusion_det.py:515-633)."""
+        hp = self.hp
+        N = self.num_proposals
+        ib = self.infer_batch
+        T = hp["sample_step"]
         batch = min(ib, infos["end_id"] - fid + 1)
         r0 = hp["key_frame_location"]
         idxs = range(r0, r0 + batch)
@@ -896,10 +925,19 @@ class DiffusionDet(nn.Module):
         # not stall the launch of the next key batch (0.13 ms of GPU idle per batch with the synchronous read).  The
         # 4-deep ring resolves the oldest batch before its slot is reused, which bounds how far the host runs ahead.
         cnt, ob, osc, ol = r["count"], r["boxes"], r["scores"], r["labels"]
-        if self._graph_active() and world == 1:       # graph-owned buffers: the next replay overwrites them
-            cnt, ob, osc, ol = cnt.clone(), ob.clone(), osc.clone(), ol.clone()
+        if self._graph_active() and (world == 1 or self._shard_mode == "batches"):
+            cnt, ob, osc, ol = cnt.clone(), ob.clone(), osc.clone(), ol.clone()   # graph-owned buffers: the next replay overwrites them
         self.io_bytes["d2h"] += 4 * batch
-        pend = _PendingDeviceBatch(cnt, ob, osc, ol)
+        # the counts start their way to the host now (pinned buffer, asynchronous, behind the batch on ITS stream) and an
+        # event marks their arrival: resolving a batch later waits for that event only - a blocking .cpu() would wait for
+        # everything queued on the caller's stream since, i.e. for the next batch's backbone
+        done = cnt_host = None
+        if dev.type == "cuda":
+            cnt_host = torch.empty((batch,), dtype=torch.int32, pin_memory=True)
+            cnt_host.copy_(cnt, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        pend = _PendingDeviceBatch(cnt, ob, osc, ol, done, cnt_host)
         slot = self._dev_ring_pos % len(self._dev_ring)
         self._dev_ring_pos += 1
         if self._dev_ring[slot] is not None:
@@ -1126,13 +1164,20 @@ class _PendingBatch:
 class _PendingDeviceBatch:
     """Detections of one key batch that stay on the device; only the per-frame counts go to the host, on demand."""
 
-    def __init__(self, count, boxes, scores, labels):
+    def __init__(self, count, boxes, scores, labels, done=None, count_host=None):
         self.count, self.boxes, self.scores, self.labels = count, boxes, scores, labels
         self.counts = None
+        self.done = done          # event behind the batch (and the copy of its counts) on the stream that produced it
+        self.count_host = count_host
 
     def resolve(self):
         if self.counts is None:
-            self.counts = [int(c) for c in self.count.cpu().tolist()]     # blocking copy behind the batch's kernels
+            if self.done is not None:
+                self.done.synchronize()      # the tensors are complete for every stream from here on
+                self.counts = [int(c) for c in self.count_host.tolist()]
+                self.count_host = None
+            else:
+                self.counts = [int(c) for c in self.count.cpu().tolist()]
         return self.counts
 
     def frame(self, i):
