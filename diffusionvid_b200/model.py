@@ -130,8 +130,12 @@ class DiffusionDet(nn.Module):
         self.streamk = bool(int(__import__("os").environ.get("DVID_STREAMK", hp.get("streamk", 0))))
         self.fused_tail = bool(hp.get("fused_tail", True))
         import os as _os
-        # DynamicConv bmm pair on tcgen05 (roi_dynconv_tc_kernel) or on mma.sync (roi_dynconv_kernel, the round-1 kernel)
-        self.dynconv_tc = bool(int(_os.environ.get("DVID_DYNCONV_TC", hp.get("dynconv_tc", 1))))
+        # DynamicConv bmm pair on tcgen05 (roi_dynconv_tc_kernel) or on mma.sync (roi_dynconv_kernel).  Both kernels take
+        # 145 us per 2400 boxes in isolation - they are bound by the fp32 bilinear gather on the CUDA cores, not by the
+        # contractions (profiles/r02_ncu_dynconv_warm.txt) - but inside the pipeline the tcgen05 variant costs 1.7 % of
+        # the step (4 % with the decode overlapping the next backbone pass: 806 vs 838 frames/s): only the four warps
+        # that own TMEM lanes 0..63 can run its LayerNorm epilogues.  Default: mma.sync; DVID_DYNCONV_TC=1 selects tcgen05.
+        self.dynconv_tc = bool(int(_os.environ.get("DVID_DYNCONV_TC", hp.get("dynconv_tc", 0))))
         self.extract_batch = int(_os.environ.get("DVID_EXTRACT_BATCH", hp.get("extract_batch", 32)))
         self.dyn_chunk_frames = int(_os.environ.get("DVID_DYN_CHUNK", hp.get("dyn_chunk_frames", 0)))
         # frames that arrive in HOST memory: run the backbone on the frames already uploaded while the later ones are

@@ -122,6 +122,27 @@ def test_clip_end_to_end_matches_oracle(cuda, T):
         assert sum(f >= 0.95 for f in fracs) >= 0.5 * L, fracs
 
 
+@pytest.mark.parametrize("T", [1, 4])
+def test_clip_with_the_tcgen05_decoder_kernels(cuda, T, monkeypatch):
+    """The opt-in tcgen05 variants of the decoder's small contractions inside the whole model: DynamicConv bmm pair
+    (roi_dynconv_tc_kernel, hp dynconv_tc / DVID_DYNCONV_TC) and head-dim-32 attention (attention_tc_kernel,
+    ops.ATTENTION_TC / DVID_ATTN_TC).  Same clip, same bar against the oracle as the default kernels."""
+    monkeypatch.setattr(ops, "ATTENTION_TC", True)
+    h, w, L = 192, 256, 19
+    hp, sd, m, noise, ocfg = _models(T, hp_over=dict(dynconv_tc=1))
+    assert m.dynconv_tc
+    o = om.OracleDiffusionVID(sd, ocfg, fp16=True, noise=noise)
+    frames = synth.make_clip(L, h, w, seed=6)
+    samples = synth.clip_samples(frames, [17, 3, 9, 12], h, w)
+    l0 = ops.LAUNCHES
+    fracs, counts_equal, n_out = _run_clip(m, o, samples, h, w, L)
+    assert n_out == L and ops.LAUNCHES > l0
+    fr = sorted(fracs)
+    assert fr[len(fr) // 2] >= 0.95, fracs
+    if T == 1:
+        assert sum(fracs) / len(fracs) >= 0.95, fracs
+
+
 def test_single_frame_config_without_global_memory(cuda):
     """BASELINE config[0] shape: vid_R_101_DiffusionDET.yaml semantics - 4 base heads, no cond head / memory, T=1,
     N=100, 2 frames of 300x300 (padded to 320x320)."""
