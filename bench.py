@@ -471,6 +471,25 @@ def run_ours(args):
         h2d_u8 = (m.io_bytes["h2d"] - io1["h2d"]) // max(1, args.steps)
         d2h_u8 = (m.io_bytes["d2h"] - io1["d2h"]) // max(1, args.steps)
         del u8_samples
+        # optional dead-code elimination (model.skip_unused_base, OFF for every other number of this line): the t=999
+        # base stages of local frames, which the reference computes but never reads when SAMPLE_STEP > 1
+        dce = None
+        if args.T > 1:
+            m.skip_unused_base = True
+            for _ in range(2):
+                run_clip(m, host_samples, True)
+            ms_d2, fr_d2, _, _ = timed(m, host_samples, args.steps, True, dist, dev)
+            m.host_results = False
+            for _ in range(2):
+                run_clip(m, dev_samples, False)
+            ms_d1, fr_d1, _, _ = timed(m, dev_samples, args.steps, False, dist, dev)
+            m.host_results = True
+            m.skip_unused_base = False
+            dce = {"value": fr_d1 * (1 if shard_frames else world) / (ms_d1 / 1000.0),
+                   "e2e": fr_d2 * (1 if shard_frames else world) / (ms_d2 / 1000.0), "unit": "frames/s",
+                   "what": "same workload and detections (bit-identical, tests/test_gpu_model.py), without the 3 base-stage "
+                           "head evaluations per local frame that diffusion_det.py:438-460 computes and only the "
+                           "SAMPLE_STEP == 1 branch (box_head.py:300-302) reads; NOT used for value / e2e / roofline"}
         # the reference's engine loop verbatim (uploads of cur + refs per call, a device synchronisation per call)
         for _ in range(2):
             run_clip_engine(m, host_samples, dev)
@@ -655,7 +674,7 @@ def run_ours(args):
                                    "per call (:35-40; cur is a second upload of a frame that also arrives as a ref), "
                                    "model(images), torch.cuda.synchronize() per call (:70-73), outputs .to(cpu) (:75)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
-            "frame_sharded": fs, "batch_sharded": bs}
+            "frame_sharded": fs, "batch_sharded": bs, "dead_code_elimination": dce}
     print(json.dumps(line))
     if dist:
         torch.distributed.destroy_process_group()

@@ -169,7 +169,17 @@ class DiffusionDet(nn.Module):
         # decode unit on its own stream, so that the (latency-bound, small-grid) decoder kernels of batch k share the GPU
         # with the dense convolutions of batch k+1 instead of queueing in front of them.
         self.overlap_decode = bool(int(_os.environ.get("DVID_OVERLAP_DECODE", hp.get("overlap_decode", 1))))
-        self._decode_stream = None
+        # number of decode streams used round-robin by consecutive key batches (each has its own captured decode graph)
+        self.decode_streams = max(1, int(_os.environ.get("DVID_DECODE_STREAMS", hp.get("decode_streams", 2))))
+        # Dead-code elimination, OFF by default (the default executes every operation of the reference): with
+        # SAMPLE_STEP > 1 the reference still runs the three base stages at t=999 on every LOCAL frame at extraction
+        # (diffusion_det.py:438-460) although their outputs - classes_300 / proposals_300 / proposals_feat_300 - are read
+        # only by the SAMPLE_STEP == 1 branch (box_head.py:300-302; local_box_enable is False); only the GLOBAL frames'
+        # top-k features feed the memory (:479-488).  With this switch on, local frames of steady-state key batches get
+        # the backbone only.  Detections are bit-identical (tests/test_gpu_model.py); bench.py reports it separately.
+        self.skip_unused_base = bool(int(_os.environ.get("DVID_SKIP_UNUSED_BASE", hp.get("skip_unused_base", 0))))
+        self._decode_stream = None          # list of streams once created
+        self._decode_turn = 0
         self.eval()
 
     # ------------------------------------------------------------------------------------------ weight packing
@@ -555,7 +565,8 @@ class DiffusionDet(nn.Module):
     def _for_decode(self, t):
         """Tensors produced on the caller's stream and read by the decode stream: tell the caching allocator."""
         if self._decode_stream is not None and t is not None and t.is_cuda:
-            t.record_stream(self._decode_stream)
+            for st in self._decode_stream:
+                t.record_stream(st)
         return t
 
     def _set_memory(self, mem):
@@ -771,7 +782,7 @@ class DiffusionDet(nn.Module):
         if dev.type == "cuda":
             ops.conv_streamk(self.streamk)       # process-wide library switch: set per call (several models may coexist)
             if self.overlap_decode and self._decode_stream is None:
-                self._decode_stream = torch.cuda.Stream()
+                self._decode_stream = [torch.cuda.Stream() for _ in range(self.decode_streams)]
         N = self.num_proposals
         ib = self.infer_batch
         if infos["frame_category"] == 0:
@@ -823,7 +834,8 @@ class DiffusionDet(nn.Module):
             host_side = lambda it: isinstance(it, tuple) or not it.tensors.is_cuda      # noqa: E731
             if (self.pipeline_uploads and world == 1 and dev.type == "cuda" and (early or n_total > ib)
                     and (self._pipeline_device or all(host_side(it) for it in all_imgs[(early[0] if early else 0):]))):
-                ex = self._extract_pipelined(all_imgs, early, fid, n_total, w, h, dev)
+                ex = self._extract_pipelined(all_imgs, early, fid, n_total, w, h, dev,
+                                             feats_only=self.skip_unused_base and T > 1 and not ref_g)
                 mine = []
             if mine:
                 # host images are copied one by one (asynchronously when pinned) and concatenated on the device
@@ -847,9 +859,14 @@ class DiffusionDet(nn.Module):
                 # per-split draw order), so up to `extract_batch` frames go through one unit: at a video start
                 # (8 local + 24 global frames) that fills the GPU far better than four 8-frame passes.
                 eb = max(ib, int(self.extract_batch))
+                feats_only = self.skip_unused_base and T > 1 and not ref_g
                 for split, binit in zip(total.split(eb), box_all.split(eb)):
-                    o = self._run_unit("extract", self._extract, (w, h),
-                                       dict(imgs=split.contiguous(), box_init=binit.contiguous()), dict(w=w, h=h))
+                    if feats_only:
+                        o = self._run_unit("features", self._features, (w, h), dict(imgs=split.contiguous()),
+                                           dict(w=w, h=h))
+                    else:
+                        o = self._run_unit("extract", self._extract, (w, h),
+                                           dict(imgs=split.contiguous(), box_init=binit.contiguous()), dict(w=w, h=h))
                     # unit outputs live in graph-owned buffers that the next replay overwrites: keep private copies
                     outs.append({k: v.clone() for k, v in o.items()} if self._graph_active() else o)
                 ex = {k: (torch.cat([o[k] for o in outs]) if len(outs) > 1 else outs[0][k]) for k in outs[0]}
@@ -868,7 +885,8 @@ class DiffusionDet(nn.Module):
                 if i in pos:
                     j = pos[i]
                     self.feats.append([self._for_decode(ex[l][j:j + 1]) for l in ("p3", "p4", "p5")])
-                    self.cache.append(tuple(self._for_decode(ex[l][j:j + 1]) for l in ("lg", "bx", "o32", "o16")))
+                    self.cache.append(tuple(self._for_decode(ex[l][j:j + 1]) for l in ("lg", "bx", "o32", "o16"))
+                                      if "lg" in ex else None)
                 else:       # another rank owns this frame
                     self.feats.append(None)
                     self.cache.append(None)
@@ -877,14 +895,17 @@ class DiffusionDet(nn.Module):
         overlap = (self.overlap_decode and dev.type == "cuda" and not self.debug_trace
                    and (world == 1 or self._shard_mode == "batches"))
         if not overlap:
-            return self._key_batch(infos, fid, w, h, dev, rank, world, None)
+            return self._key_batch(infos, fid, w, h, dev, rank, world, None, 0)
         ev = torch.cuda.Event()
         ev.record()                                   # everything the decode reads has been enqueued before this point
-        self._decode_stream.wait_event(ev)
-        with torch.cuda.stream(self._decode_stream):
-            return self._key_batch(infos, fid, w, h, dev, rank, world, self._decode_stream)
+        turn = self._decode_turn % len(self._decode_stream)
+        self._decode_turn += 1
+        st = self._decode_stream[turn]
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
+            return self._key_batch(infos, fid, w, h, dev, rank, world, st, turn)
 
-    def _key_batch(self, infos, fid, w, h, dev, rank, world, stream):
+    def _key_batch(self, infos, fid, w, h, dev, rank, world, stream, turn):
         """DDIM decode + post-processing + result hand-over of one key batch (diffusion_det.py:515-633)."""
         hp = self.hp
         N = self.num_proposals
@@ -916,7 +937,7 @@ class DiffusionDet(nn.Module):
                 self.last_trace = {}
                 r = self._decode(**tensors, **consts, trace=self.last_trace, fid=fid)
             else:
-                r = self._run_unit("decode", self._decode, (w, h), tensors, consts)
+                r = self._run_unit("decode", self._decode, (w, h, turn), tensors, consts)
         if world > 1 and self._shard_mode == "batches":
             if r is None:
                 return []          # another rank's key batch: its owner returns (and later contributes) the results
@@ -961,7 +982,7 @@ class DiffusionDet(nn.Module):
         o = self._run_unit("features", self._features, (w, h), dict(imgs=x), dict(w=w, h=h))
         return {k: v.clone() for k, v in o.items()} if self._graph_active() else o
 
-    def _extract_pipelined(self, all_imgs, early, fid, n_total, w, h, dev):
+    def _extract_pipelined(self, all_imgs, early, fid, n_total, w, h, dev, feats_only=False):
         """`_extract` for frames that come from host memory: every upload is issued first (copy stream, arrival order),
         then the backbone runs chunk by chunk as the chunks land - PCIe time hides behind the previous chunk's compute
         instead of preceding the whole batch - and the base stages run once over all frames.  Per-frame results are
@@ -974,6 +995,8 @@ class DiffusionDet(nn.Module):
         for c0 in range(0, len(rest), csz):
             feats.append(self._features_of(rest[c0:c0 + csz], w, h, dev))
         f = {k: (torch.cat([x[k] for x in feats]) if len(feats) > 1 else feats[0][k]) for k in ("p3", "p4", "p5")}
+        if feats_only:
+            return f
         inits = [self._randn("init", fid, bi, min(ib, n_total - bi * ib), dev) for bi in range((n_total + ib - 1) // ib)]
         box_all = torch.cat(inits) if len(inits) > 1 else inits[0]
         eb = max(ib, int(self.extract_batch))

@@ -143,6 +143,35 @@ def test_clip_with_the_tcgen05_decoder_kernels(cuda, T, monkeypatch):
         assert sum(fracs) / len(fracs) >= 0.95, fracs
 
 
+def test_skipping_the_unused_base_stages_changes_nothing(cuda):
+    """hp skip_unused_base (dead-code elimination, off by default): with SAMPLE_STEP > 1 the t=999 base stages of the
+    LOCAL frames are computed by the reference (diffusion_det.py:438-460) but read only by the SAMPLE_STEP == 1 branch
+    (box_head.py:300-302).  Skipping them must give bit-identical detections, device-resident and host-fed."""
+    h, w, L = 192, 256, 27
+    outs = []
+    for skip in (0, 1):
+        for host in (False, True):
+            hp, sd, m, noise, ocfg = _models(4, hp_over=dict(skip_unused_base=skip))
+            m.host_results = host
+            frames = synth.make_clip(L, h, w, seed=6)
+            frames = frames.pin_memory() if host else frames.to(cuda)
+            res = []
+            l0 = ops.LAUNCHES
+            for s in synth.clip_samples(frames, [17, 3, 9, 12], h, w):
+                got = m(dict(cur=structures.ImageList(s["cur"], [(h, w)]),
+                             ref_l=[structures.ImageList(t, [(h, w)]) for t in s["ref_l"]],
+                             ref_g=[structures.ImageList(t, [(h, w)]) for t in s["ref_g"]],
+                             frame_id=s["frame_id"], start_id=0, end_id=s["end_id"], seg_len=L,
+                             frame_category=s["frame_category"], video_id=0))
+                res += [(b.bbox.cpu(), b.get_field("scores").cpu(), b.get_field("labels").cpu()) for b in got]
+            outs.append((res, ops.LAUNCHES - l0))
+    assert all(len(o[0]) == L for o in outs)
+    for k in (0, 1):        # same feeding mode, with / without the dead work
+        for (b0, s0, l0), (b1, s1, l1) in zip(outs[k][0], outs[2 + k][0]):
+            assert torch.equal(b0, b1) and torch.equal(s0, s1) and torch.equal(l0, l1)
+        assert outs[2 + k][1] < outs[k][1]            # and it really launches fewer kernels
+
+
 def test_single_frame_config_without_global_memory(cuda):
     """BASELINE config[0] shape: vid_R_101_DiffusionDET.yaml semantics - 4 base heads, no cond head / memory, T=1,
     N=100, 2 frames of 300x300 (padded to 320x320)."""
