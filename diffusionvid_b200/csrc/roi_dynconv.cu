@@ -208,7 +208,19 @@ __device__ __forceinline__ void build_tap_table(const RoiGeom& gm, TapTable& tb,
   }
 }
 
+// fp32 += fp16 * fp16 in ONE instruction (FHFMA, PTX mixed-precision fma): the product of two halfs is exact in fp32.
+__device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+
 // Gather one bin with the calling warp from the tap table (all <= 16 taps in flight before the first is consumed).
+// kHalfW: the tap weight is rounded to fp16 and applied with FHFMA - 8 instructions per tap instead of 8 conversions +
+// 8 FFMA (the gather is instruction-issue bound).  The fp16 x fp16 product is exact and the accumulation stays fp32; the
+// only difference to the fp32-weight path is the rounding of the weight (<= 2^-12 relative per tap, i.e. at most half an
+// fp16 ulp of the fp16-rounded result).
+template <bool kHalfW>
 __device__ __forceinline__ void roi_bin_table(const RoiGeom& gm, const TapTable& tb, int bin, int lane,
                                               float (&acc)[8]) {
   const int ph = bin / P, pw = bin - ph * P;
@@ -239,12 +251,22 @@ __device__ __forceinline__ void roi_bin_table(const RoiGeom& gm, const TapTable&
     for (int ix = 0; ix < 4; ++ix) {
       if (xwt[ix] != 0.f) {
         const float wgt = ywt[iy] * xwt[ix];
-        const __half2* hp = reinterpret_cast<const __half2*>(&v[iy][ix]);
+        if (kHalfW) {
+          const unsigned short wh = __half_as_ushort(__float2half_rn(wgt));
+          const uint32_t w4[4] = {v[iy][ix].x, v[iy][ix].y, v[iy][ix].z, v[iy][ix].w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(hp[e]);
-          acc[2 * e] = fmaf(wgt, f.x, acc[2 * e]);
-          acc[2 * e + 1] = fmaf(wgt, f.y, acc[2 * e + 1]);
+          for (int e = 0; e < 4; ++e) {
+            acc[2 * e] = fhfma(static_cast<unsigned short>(w4[e] & 0xffffu), wh, acc[2 * e]);
+            acc[2 * e + 1] = fhfma(static_cast<unsigned short>(w4[e] >> 16), wh, acc[2 * e + 1]);
+          }
+        } else {
+          const __half2* hp = reinterpret_cast<const __half2*>(&v[iy][ix]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hp[e]);
+            acc[2 * e] = fmaf(wgt, f.x, acc[2 * e]);
+            acc[2 * e + 1] = fmaf(wgt, f.y, acc[2 * e + 1]);
+          }
         }
       }
     }
@@ -323,7 +345,7 @@ __device__ __forceinline__ void row_allreduce(float (&part)[2], float* sstat, in
   part[1] = sstat[(row0 + g + 8) * 2] + sstat[(row0 + g + 8) * 2 + 1];
 }
 
-template <bool kRoiFromGlobal>
+template <bool kRoiFromGlobal, bool kHalfW = false>
 __global__ void __launch_bounds__(256, 2)
 roi_dynconv_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_frame,
                    const __half* __restrict__ roi_in,      // [M][49][256] (kRoiFromGlobal)
@@ -376,7 +398,7 @@ roi_dynconv_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_
     __syncthreads();
     for (int bin = warp; bin < NBIN; bin += 8) {
       float acc[8];
-      roi_bin_table(gm, taps, bin, lane, acc);
+      roi_bin_table<kHalfW>(gm, taps, bin, lane, acc);
       *reinterpret_cast<uint4*>(sRoi + off512(bin, lane)) = pack8(acc);
     }
   }
@@ -601,7 +623,7 @@ roi_dynconv_tc_kernel(const __grid_constant__ DynMaps maps, RoiLevels lv, const 
     __syncthreads();
     for (int bin = warp; bin < NBIN; bin += 8) {
       float acc[8];
-      roi_bin_table(gm, taps, bin, lane, acc);
+      roi_bin_table<false>(gm, taps, bin, lane, acc);
       *reinterpret_cast<uint4*>(roi_dst(bin, lane)) = pack8(acc);
     }
   }
@@ -787,11 +809,21 @@ int roi_dynconv_launch(const void* const* feats, const int* hs, const int* ws, c
     if (cudaFuncSetAttribute(roi_dynconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) !=
             cudaSuccess ||
         cudaFuncSetAttribute(roi_dynconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(roi_dynconv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) !=
             cudaSuccess)
       return DVID_ERR_CUDA;
     attr_set = true;
   }
+  static int half_w = -1;
+  if (half_w < 0) { const char* e = getenv("DVID_ROI_F16W"); half_w = e ? atoi(e) : 0; }
   const RoiLevels lv = make_levels(feats, hs, ws, scales);
+  if (roi_in == nullptr && half_w) {
+    launch_pdl(roi_dynconv_kernel<false, true>, dim3(num_boxes), dim3(256), SM_TOTAL, stream,
+        lv, boxes, boxes_per_frame, nullptr, static_cast<const __half*>(params), g1, b1, g2, b2,
+        static_cast<__half*>(out));
+    return check_launch();
+  }
   if (roi_in != nullptr) {
     launch_pdl(roi_dynconv_kernel<true>, dim3(num_boxes), dim3(256), SM_TOTAL, stream, 
         lv, boxes, boxes_per_frame, static_cast<const __half*>(roi_in), static_cast<const __half*>(params), g1, b1,
