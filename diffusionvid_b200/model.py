@@ -826,7 +826,7 @@ class DiffusionDet(nn.Module):
             n_total, len_l = len(all_imgs), len(ref_l)
             # sharding of one clip (SURVEY.md 8e mode B): see set_frame_sharding for the two ownership rules
             kb_index = (fid - infos.get("start_id", 0)) // ib
-            owner = [self._frame_owner(i, len_l, kb_index, world) for i in range(n_total)]
+            owner = self._frame_owners(n_total, len_l, kb_index, world)
             mine = [i for i in range(n_total) if owner[i] == rank]
             pos = {g: j for j, g in enumerate(mine)}
             ex = None
@@ -1088,15 +1088,23 @@ class DiffusionDet(nn.Module):
         self._shard = (int(rank), int(world), group) if world > 1 else None
         self._shard_mode = mode
 
-    def _frame_owner(self, i, len_l, key_batch, world):
-        """Rank that owns frame i of a key call's [local..., global...] list."""
+    def _frame_owners(self, n_total, len_l, key_batch, world):
+        """Rank that owns each frame of a key call's [local..., global...] list (identical on every rank)."""
         if world == 1:
-            return 0
+            return [0] * n_total
         if self._shard_mode == "frames":
-            return i % world
-        if i < len_l:
-            return key_batch % world
-        return (i - len_l + 1) % world       # global frames: start behind the owner of batch 0, which has 8 local frames
+            return [i % world for i in range(n_total)]
+        # whole key batches: the local frames go to the batch's owner; the global frames of the video start are dealt to
+        # the least-loaded rank (lowest rank on ties), so the owner of batch 0 - which already has 8 local frames - does
+        # not hold back the all-gather of the memory candidates
+        owner = [key_batch % world] * len_l
+        load = [0] * world
+        load[key_batch % world] += len_l
+        for _ in range(n_total - len_l):
+            r = min(range(world), key=lambda k: (load[k], k))
+            owner.append(r)
+            load[r] += 1
+        return owner
 
     def _gather_global_candidates(self, ex, pos, len_l, n_total, dev, owner=None):
         """(G*75,256) / (G*25,256) memory candidates of the global frames in frame order (diffusion_det.py:476-488)."""

@@ -236,3 +236,21 @@ def test_deferred_boxlist_resolves_on_first_access():
 def test_package_exports():
     assert diffusionvid_b200.__version__
     assert hasattr(diffusionvid_b200, "build_detection_model")
+
+
+def test_frame_ownership_rules_of_the_two_sharding_modes():
+    """DiffusionDet._frame_owners: "frames" deals every frame of a call round-robin; "batches" gives the local frames to
+    the key batch's owner and deals the global frames of the video start to the least-loaded rank."""
+    m = pm.DiffusionDet(dict(SMALL))
+    m.set_frame_sharding(0, 4, mode="frames")
+    assert m._frame_owners(10, 8, 0, 4) == [0, 1, 2, 3, 0, 1, 2, 3, 0, 1]
+    m.set_frame_sharding(0, 4, mode="batches")
+    own = m._frame_owners(8 + 24, 8, 0, 4)
+    assert own[:8] == [0] * 8
+    assert [own.count(r) for r in range(4)] == [8, 8, 8, 8]          # 8 local on rank 0, the 24 global on ranks 1..3
+    assert m._frame_owners(8, 8, 5, 4) == [1] * 8                     # steady state: batch 5 -> rank 5 % 4
+    m.set_frame_sharding(0, 2, mode="batches")
+    own = m._frame_owners(8 + 24, 8, 0, 2)
+    assert [own.count(r) for r in range(2)] == [16, 16] and own[8:16] == [1] * 8
+    with pytest.raises(ValueError):
+        m.set_frame_sharding(0, 2, mode="videos")
