@@ -34,6 +34,7 @@ SIGNATURES = {
     "dvid_roi_align": [P, P, P, P, P, I, I, P, P, P, P],
     "dvid_roi_dynconv": [P, P, P, P, P, I, I, P, P, P, P, P, P, P, P],
     "dvid_roi_dynconv_tc": [P, P, P, P, P, I, I, P, P, P, P, P, P, P, P],
+    "dvid_gemm256_row": [P, P, P, P, P, P, I, P, P, I, P],
     "dvid_row_post": [P, I, L, P, P, P, P, I, P, P, P, I, I, P, P, P, P, I, I, I, I, P, I, P],
     "dvid_small_linear": [P, P, P, P, I, I, I, I, I, P],
     "dvid_time_sinusoid": [P, P, P, I, P],

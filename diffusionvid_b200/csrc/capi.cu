@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 13
+#define DVID_ABI_VERSION 14
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -268,6 +268,12 @@ int dvid_swin_window_attention(const void* qkv, const float* bias, void* out_f16
                                int heads, int shift, void* stream) {
   if (!qkv || !bias || !out_f16) return DVID_ERR_ARG;
   return dvid::swin_window_attention_launch(qkv, bias, out_f16, B, H, W, C, heads, shift, S(stream));
+}
+
+int dvid_gemm256_row(const void* a, const void* w, const float* bias, const float* resid, const float* ln_g,
+                     const float* ln_b, int act, float* out_f32, void* out_f16, int m, void* stream) {
+  if (!a || !w || (!out_f32 && !out_f16) || (ln_g && !ln_b)) return DVID_ERR_ARG;
+  return dvid::gemm256_row_launch(a, w, bias, resid, ln_g, ln_b, act, out_f32, out_f16, m, S(stream));
 }
 
 int dvid_swin_window_attention_tc(const void* qkv, const float* bias, void* out_f16, int B, int H, int W, int C,

@@ -130,6 +130,12 @@ class DiffusionDet(nn.Module):
         self.streamk = bool(int(__import__("os").environ.get("DVID_STREAMK", hp.get("streamk", 0))))
         self.fused_tail = bool(hp.get("fused_tail", True))
         import os as _os
+        # 256->256 Linears fused with their bias / residual / LayerNorm / SiLU epilogue (gemm_row.cu) instead of a
+        # partial-sum GEMM + a row kernel
+        # (measured: 824 vs 836 frames/s - the fused kernel runs on 19 CTAs with a serial load -> MMA -> two-pass epilogue
+        # chain, the GEMM + row kernel pair on 76 + 300 CTAs overlapped by programmatic dependent launch - so it is the
+        # opt-in)
+        self.fused_rows = bool(int(_os.environ.get("DVID_FUSED_ROWS", hp.get("fused_rows", 0))))
         # DynamicConv bmm pair on tcgen05 (roi_dynconv_tc_kernel) or on mma.sync (roi_dynconv_kernel).  Both kernels take
         # 145 us per 2400 boxes in isolation - they are bound by the fp32 bilinear gather on the CUDA cores, not by the
         # contractions (profiles/r02_ncu_dynconv_warm.txt) - but inside the pipeline the tcgen05 variant costs 1.7 % of
@@ -450,8 +456,11 @@ class DiffusionDet(nn.Module):
             ctx = torch.empty((M, 256), device=dev, dtype=H)
             ops.attention(qkv, qkv[:, 256:], qkv[:, 512:], ctx, B, 8, N, N, 768, 768, 768, 256, N * 768, N * 768,
                           N * 768, N * 256)
-            part, s = ops.gemm_partials(ctx, e["out_w"], 1)
             p32 = torch.empty((M, 256), device=dev, dtype=F32); p16 = torch.empty((M, 256), device=dev, dtype=H)
+            if self.fused_rows:     # out_proj + bias + residual + norm1 in one tcgen05 kernel
+                ops.gemm_row(ctx, e["out_w"], bias=e["out_b"], resid=pro32, ln=e["n1"], out_f32=p32, out_f16=p16)
+                return p32, p16
+            part, s = ops.gemm_partials(ctx, e["out_w"], 1)
             ops.row_post(M, partials=part, splits=s, bias=e["out_b"], resid=pro32, ln2=e["n1"], out_f32=p32,
                          out_f16=p16)
             return p32, p16
@@ -536,15 +545,21 @@ class DiffusionDet(nn.Module):
         kv = self._mem_kv if kv is None else kv
         ctx = torch.empty((M, 256), device=dev, dtype=H)
         ops.attention(q, kv, kv[:, 256:], ctx, 1, 8, M, kv.shape[0], 256, 512, 512, 256, 0, 0, 0, 0)
-        part, s = ops.gemm_partials(ctx, ga["o_w"], 1)
         cond16 = torch.empty((M, 256), device=dev, dtype=H)
+        if self.fused_rows:
+            ops.gemm_row(ctx, ga["o_w"], bias=ga["o_b"], act=2, out_f16=cond16)
+            return cond16
+        part, s = ops.gemm_partials(ctx, ga["o_w"], 1)
         ops.row_post(M, partials=part, splits=s, bias=ga["o_b"], act2=2, act2_f16_only=True, out_f16=cond16)
         return cond16
 
     def _cond_shift(self, e, cond16, M):
         """c_mlp of cond head `e` on SiLU(attn_) (box_head.py:644): the per-row shift (M,256) fp32."""
-        part, s = ops.gemm_partials(cond16, e["cm_w"], 1)
         shift = torch.empty((M, 256), device=cond16.device, dtype=F32)
+        if self.fused_rows:
+            ops.gemm_row(cond16, e["cm_w"], bias=e["cm_b"], out_f32=shift)
+            return shift
+        part, s = ops.gemm_partials(cond16, e["cm_w"], 1)
         ops.row_post(M, partials=part, splits=s, bias=e["cm_b"], out_f32=shift)
         return shift
 

@@ -261,6 +261,21 @@ def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=N
     return out
 
 
+def gemm_row(a, w, bias=None, resid=None, ln=None, act=0, out_f32=None, out_f16=None):
+    """Fused 256->256 Linear + bias [+ residual] [+ LayerNorm]: out_f32 = y, out_f16 = act(y) (dvid_gemm256_row)."""
+    _chk(a, H, "a"); _chk(w, H, "w"); _chk(bias, F32, "bias"); _chk(resid, F32, "resid")
+    _chk(out_f32, F32, "out_f32"); _chk(out_f16, H, "out_f16")
+    m, k = a.shape
+    if k != 256 or tuple(w.shape) != (256, 256):
+        raise _lib.DvidError("gemm_row: a [m][256], w [256][256]")
+    g, b = ln if ln is not None else (None, None)
+    with _prof("conv_gemm", 2.0 * m * 256 * 256, 2.0 * (m * 256 + 65536) + 6.0 * m * 256,
+               tag="gemm+row %dx256->256" % m):
+        check(_lib.lib().dvid_gemm256_row(ptr(a), ptr(w), ptr(bias), ptr(resid), ptr(g), ptr(b), int(act), ptr(out_f32),
+                                          ptr(out_f16), m, cur_stream()), "dvid_gemm256_row")
+    _cnt()
+
+
 def row_post(M, partials=None, splits=1, in_f16=None, bias=None, ln1=None, relu1=False, resid=None, ln2=None, act2=0,
              act2_f16_only=False, out_f32=None, out_f16=None, mod_scale=None, mod_shift=None, rows_per_group=1,
              scale_stride=0, shift_stride=0, shift_per_row=False, out_mod_f16=None):

@@ -133,6 +133,13 @@ DVID_API int dvid_roi_dynconv_tc(const void* const* feats, const int* hs, const 
                         const void* params_t, const float* ln1_g, const float* ln1_b, const float* ln2_g,
                         const float* ln2_b, void* out, void* stream);
 
+/* 256 -> 256 Linear fused with its row epilogue (csrc/gemm_row.cu): y = a @ w^T + bias [+ resid] -> [LayerNorm(ln_g, ln_b)]
+ * -> out_f32 = y, out_f16 = act(y) (act: 0 none, 1 ReLU, 2 SiLU).  a [m][256] fp16, w [256][256] fp16, resid / out_f32
+ * fp32 [m][256].  Replaces nn.Linear + residual + nn.LayerNorm at box_head.py:516-518 / :626-628 (self_attn.out_proj,
+ * norm1) and the two Linears around the SiLU at :371 / :644 (global attention out_proj, c_mlp). */
+DVID_API int dvid_gemm256_row(const void* a, const void* w, const float* bias, const float* resid, const float* ln_g,
+                     const float* ln_b, int act, float* out_f32, void* out_f16, int m, void* stream);
+
 /* Row kernel for 256-wide rows: y = sum_s partials[s] (or in_f16) + bias -> [LN1] -> [ReLU] -> [+resid] -> [LN2] ->
  * act2 (0 none / 1 ReLU / 2 SiLU; on the fp16 output only if act2_f16_only) -> out_f32 / out_f16; optional time /
  * condition modulation out_mod_f16 = y * (scale[row / rows_per_group] + 1) + shift (box_head.py:533-536, :643-647).

@@ -136,6 +136,18 @@ def roi_dynconv(levels, boxes, boxes_per_frame, params, g1, b1, g2, b2, roi_in=N
     return f
 
 
+def gemm_row(a, w, bias=None, resid=None, ln=None, act=0, out_f32=None, out_f16=None):
+    y = F.linear(a.float(), w.float(), bias)
+    if resid is not None:
+        y = y + resid
+    if ln is not None:
+        y = F.layer_norm(y, (256,), ln[0], ln[1])
+    if out_f32 is not None:
+        out_f32.copy_(y)
+    if out_f16 is not None:
+        out_f16.copy_((F.relu(y) if act == 1 else F.silu(y) if act == 2 else y).half())
+
+
 def row_post(M, partials=None, splits=1, in_f16=None, bias=None, ln1=None, relu1=False, resid=None, ln2=None, act2=0,
              act2_f16_only=False, out_f32=None, out_f16=None, mod_scale=None, mod_shift=None, rows_per_group=1,
              scale_stride=0, shift_stride=0, shift_per_row=False, out_mod_f16=None):

@@ -133,6 +133,36 @@ def test_roi_dynconv(cuda, fused, tc):
     assert (got - ref).abs().mean().item() <= 1e-3
 
 
+@pytest.mark.parametrize("M", [2400, 300, 77])
+@pytest.mark.parametrize("mode", ["resid_ln", "silu", "plain"])
+def test_gemm_row_fused_linear_epilogue(cuda, M, mode):
+    """dvid_gemm256_row: out_proj + residual + norm1 (box_head.py:516-518), global-attention out_proj + SiLU (:371, :644),
+    c_mlp Linear (:644) - against fp32 torch math on the fp16-rounded operands."""
+    g = gen(23 + M)
+    a = torch.randn(M, 256, generator=g).half()
+    w = (torch.randn(256, 256, generator=g) / 16).half()
+    b = 0.1 * torch.randn(256, generator=g)
+    resid = torch.randn(M, 256, generator=g)
+    ln = (1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g))
+    y = F.linear(a.float(), w.float(), b)
+    o32 = torch.full((M, 256), 7.0, device=cuda)
+    o16 = torch.full((M, 256), 7.0, device=cuda, dtype=torch.float16)
+    if mode == "resid_ln":
+        ref = F.layer_norm(y + resid, (256,), ln[0], ln[1])
+        ops.gemm_row(a.to(cuda), w.to(cuda), bias=b.to(cuda), resid=resid.to(cuda), ln=(ln[0].to(cuda), ln[1].to(cuda)),
+                     out_f32=o32, out_f16=o16)
+        assert (o32.cpu() - ref).abs().max().item() <= 2e-3
+        assert (o16.float().cpu() - ref).abs().max().item() <= 6e-3
+    elif mode == "silu":
+        ops.gemm_row(a.to(cuda), w.to(cuda), bias=b.to(cuda), act=2, out_f16=o16)
+        assert (o16.float().cpu() - F.silu(y)).abs().max().item() <= 6e-3
+        assert torch.all(o32 == 7.0)
+    else:
+        ops.gemm_row(a.to(cuda), w.to(cuda), bias=b.to(cuda), out_f32=o32)
+        assert (o32.cpu() - y).abs().max().item() <= 1e-3
+        assert torch.all(o16 == 7.0)
+
+
 # ------------------------------------------------------------------------------------------------ row kernels
 def test_row_post_variants(cuda):
     g = gen(17)
