@@ -24,5 +24,5 @@ for p in "${pids[@]:-}"; do
   if [ -n "$p" ] && ! wait "$p"; then fail=1; fi
 done
 if [ "$fail" -ne 0 ]; then echo "build.sh: compilation failed" >&2; exit 1; fi
-$NVCC -shared -o "$OUT/libdvid_b200.so" "${objs[@]}"
+$NVCC -shared -o "$OUT/libdvid_b200.so" "${objs[@]}" -ldl
 echo "built $OUT/libdvid_b200.so"

@@ -56,6 +56,8 @@ SIGNATURES = {
     "dvid_resize_workspace_bytes": [I, I, I, I, I],
     "dvid_resize_bilinear_u8": [P, I, I, I, I, I, P, I, I, P, L, P],
     "dvid_swin_window_attention": [P, P, P, I, I, I, I, I, I, P],
+    "dvid_jpeg_info": [P, L, P, P],
+    "dvid_jpeg_decode_rgb": [P, L, P, I, I, P],
     "dvid_swin_window_attention_tc": [P, P, P, I, I, I, I, I, I, P],
 }
 

@@ -53,3 +53,10 @@ class GpuFrameTransform:
         oh, ow = get_size((w, h), self.min_size, self.max_size)
         planes = ops.resize_frames_u8(frames.contiguous(), oh, ow, pad_to=self.size_divisible)
         return ImageList(planes, [(oh, ow)] * n)
+
+    def from_jpeg(self, files):
+        """Compressed frames (an iterable of JPEG byte strings of one video, all the same size) -> the same ImageList:
+        nvJPEG decode on the GPU (ops.decode_jpeg), then the resize above.  Only the compressed bytes cross PCIe."""
+        frames = [ops.decode_jpeg(f, self.device) for f in files]
+        self.h2d_bytes += sum(len(f) for f in files)
+        return self(torch.stack(frames))

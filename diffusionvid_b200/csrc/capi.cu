@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 14
+#define DVID_ABI_VERSION 15
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -268,6 +268,17 @@ int dvid_swin_window_attention(const void* qkv, const float* bias, void* out_f16
                                int heads, int shift, void* stream) {
   if (!qkv || !bias || !out_f16) return DVID_ERR_ARG;
   return dvid::swin_window_attention_launch(qkv, bias, out_f16, B, H, W, C, heads, shift, S(stream));
+}
+
+int dvid_jpeg_info(const unsigned char* data, long nbytes, int* width, int* height) {
+  if (!data || nbytes <= 0 || !width || !height) return DVID_ERR_ARG;
+  return dvid::jpeg_info(data, nbytes, width, height);
+}
+
+int dvid_jpeg_decode_rgb(const unsigned char* data, long nbytes, unsigned char* dst_hwc, int width, int height,
+                         void* stream) {
+  if (!data || nbytes <= 0 || !dst_hwc || width <= 0 || height <= 0) return DVID_ERR_ARG;
+  return dvid::jpeg_decode_rgb(data, nbytes, dst_hwc, width, height, S(stream));
 }
 
 int dvid_gemm256_row(const void* a, const void* w, const float* bias, const float* resid, const float* ln_g,

@@ -101,6 +101,10 @@ int swin_patch_gather_launch(const void* img, int is_u8, void* out, int B, int H
 int swin_window_attention_launch(const void* qkv, const float* bias, void* out, int B, int H, int W, int C, int heads,
                                  int shift, cudaStream_t stream);
 
+int jpeg_info(const unsigned char* data, long nbytes, int* width, int* height);
+int jpeg_decode_rgb(const unsigned char* data, long nbytes, unsigned char* dst_hwc, int width, int height,
+                    cudaStream_t stream);
+
 int gemm256_row_launch(const void* a, const void* w, const float* bias, const float* resid, const float* gamma,
                        const float* beta, int act, float* out_f32, void* out_f16, int M, cudaStream_t stream);
 

@@ -522,3 +522,16 @@ def roi_align_legacy_forward(inp, rois, spatial_scale, pooled_height, pooled_wid
                                                    ptr(out), cur_stream()), "dvid_roi_align_legacy_forward")
     _cnt()
     return out
+
+
+def decode_jpeg(data, device="cuda"):
+    """One JPEG file (bytes) -> uint8 [H, W, 3] RGB on the device (nvJPEG behind dvid_jpeg_decode_rgb): what
+    `Image.open(f).convert("RGB")` returns in the reference's datasets, decoded on the GPU."""
+    buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+    w, h = ctypes.c_int(0), ctypes.c_int(0)
+    check(_lib.lib().dvid_jpeg_info(buf, len(data), ctypes.byref(w), ctypes.byref(h)), "dvid_jpeg_info")
+    out = torch.empty((h.value, w.value, 3), device=device, dtype=torch.uint8)
+    check(_lib.lib().dvid_jpeg_decode_rgb(buf, len(data), ptr(out), w.value, h.value, cur_stream()),
+          "dvid_jpeg_decode_rgb")
+    _cnt()
+    return out

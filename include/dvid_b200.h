@@ -270,6 +270,17 @@ DVID_API int dvid_swin_window_attention(const void* qkv, const float* bias, void
 DVID_API int dvid_swin_window_attention_tc(const void* qkv, const float* bias, void* out_f16, int B, int H, int W, int C,
                                   int heads, int shift, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * JPEG decode in front of the clip loader, csrc/jpeg_decode.cu: nvJPEG (CUDA toolkit library, opened with
+ * dlopen on first use; DVID_ERR_DRIVER when it is not installed).  Replaces PIL's Image.open(...).convert("RGB") of the
+ * reference's datasets (mega_core/data/datasets/vid.py) for baseline / progressive JPEG files.
+ */
+/* width / height of the JPEG in `data` (HOST memory, nbytes long). */
+DVID_API int dvid_jpeg_info(const unsigned char* data, long nbytes, int* width, int* height);
+/* Decode into dst_hwc (DEVICE memory, [height][width][3] uint8, RGB interleaved) on `stream`; `data` is host memory. */
+DVID_API int dvid_jpeg_decode_rgb(const unsigned char* data, long nbytes, unsigned char* dst_hwc, int width, int height,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -509,3 +509,44 @@ def test_gpu_frame_transform_feeds_the_uint8_entry(cuda):
     ref = torch.zeros(2, 3, 160, 256); ref[:, :, :oh, :ow] = torch.from_numpy(want).float().div(255)
     b = ops.preprocess(ref.to(cuda), mean, std, halo=3)
     assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+# ------------------------------------------------------------------------------------------------ JPEG front end
+def test_jpeg_decode_feeds_the_clip_loader(cuda):
+    """dvid_jpeg_decode_rgb (nvJPEG) against Pillow's decoder on the same files - the reference's datasets decode with
+    `Image.open(f).convert("RGB")`.  JPEG decoders are not bit-identical (IDCT rounding, chroma upsampling filters):
+    4:4:4 files agree within 2 grey levels (mean < 0.5), 4:2:0 files within a mean of 2 levels.  Then the decoded frames
+    go through GpuFrameTransform exactly like frames decoded on the host."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from diffusionvid_b200 import clip_loader
+    from diffusionvid_b200._lib import DvidError
+    frames = (synth.make_clip(3, 360, 640, seed=3, pad_to=1) * 255.0).round().clamp(0, 255).to(torch.uint8)
+    files = {}
+    for sub, name in ((0, "444"), (2, "420")):
+        files[name] = []
+        for f in frames:
+            buf = io.BytesIO()
+            Image.fromarray(f.permute(1, 2, 0).numpy()).save(buf, format="JPEG", quality=92, subsampling=sub)
+            files[name].append(buf.getvalue())
+    try:
+        got = ops.decode_jpeg(files["444"][0], cuda)
+    except DvidError as e:
+        if "DVID_ERR_DRIVER" in str(e):
+            pytest.skip("libnvjpeg not installed on this machine")
+        raise
+    for name, tol_max, tol_mean in (("444", 2, 0.5), ("420", 255, 2.0)):
+        for data in files[name]:
+            got = ops.decode_jpeg(data, cuda).cpu().numpy().astype(np.int32)
+            ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB")).astype(np.int32)
+            assert got.shape == ref.shape == (360, 640, 3)
+            d = np.abs(got - ref)
+            assert d.max() <= tol_max and d.mean() <= tol_mean, (name, d.max(), d.mean())
+    loader = clip_loader.GpuFrameTransform(600, 1000, 32, device=cuda)
+    il = loader.from_jpeg(files["444"])
+    host = torch.stack([ops.decode_jpeg(f, cuda) for f in files["444"]])
+    il2 = loader(host)
+    assert il.tensors.dtype == torch.uint8 and il.tensors.shape == il2.tensors.shape and il.tensors.shape[0] == 3
+    assert torch.equal(il.tensors, il2.tensors) and il.image_sizes == il2.image_sizes
+    assert loader.h2d_bytes == sum(len(f) for f in files["444"])      # only the compressed bytes crossed PCIe
