@@ -40,7 +40,7 @@ constexpr int OFF_P = OFF_VT + 2 * SVT_BYTES;
 constexpr int OFF_BAR = OFF_P + SP_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int COL_S = 0, COL_O = 2 * KC;
-constexpr int THREADS = 192;                  // warps 0..3 softmax, 4 MMA issue, 5 tile loader
+constexpr int THREADS = 224;                  // warps 0..3 softmax, 4 MMA issue, 5 and 6 tile loaders (odd / even chunks)
 
 // 2^x for x <= 0 (softmax arguments after the running-max shift): one MUFU, denormal results flush to zero
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -138,6 +138,47 @@ __device__ __forceinline__ void load_vt_chunk(uint8_t* dst, const __half* v, int
   }
 }
 
+// K and V^T tiles of one chunk by ONE warp with every request in flight before the first store: one L2 round trip per
+// chunk (28 x 16 bytes per lane), so that the loader warp keeps ahead of the softmax chain.
+__device__ __forceinline__ void load_kv_chunk_warp(uint8_t* dk, uint8_t* dvt, const __half* k, const __half* v, int key0k,
+                                                   int key0v, int Lk, long k_rs, long v_rs, int lane) {
+  constexpr int PK = (KC * 4) / 32;                 // 14 K chunks per lane
+  constexpr int PV = (KC / 8);                      // 14 passes of 4 (8-key block, chunk) items
+  const int g = lane >> 3, i = lane & 7;
+  uint4 kv[PK], vv[PV];
+#pragma unroll
+  for (int p = 0; p < PK; ++p) {
+    const int id = lane + p * 32;
+    const int row = id >> 2, c = id & 3;
+    kv[p] = make_uint4(0, 0, 0, 0);
+    if (key0k + row < Lk) kv[p] = __ldg(reinterpret_cast<const uint4*>(k + static_cast<long>(key0k + row) * k_rs + c * 8));
+  }
+#pragma unroll
+  for (int p = 0; p < PV; ++p) {
+    const int item = p * 4 + g;
+    const int key = (item >> 2) * 8 + i, c = item & 3;
+    vv[p] = make_uint4(0, 0, 0, 0);
+    if (key0v + key < Lk) vv[p] = __ldg(reinterpret_cast<const uint4*>(v + static_cast<long>(key0v + key) * v_rs + c * 8));
+  }
+#pragma unroll
+  for (int p = 0; p < PK; ++p) {
+    const int id = lane + p * 32;
+    const int row = id >> 2, c = id & 3;
+    *reinterpret_cast<uint4*>(dk + row * 128 + ((c ^ (row & 7)) << 4)) = kv[p];
+  }
+#pragma unroll
+  for (int p = 0; p < PV; ++p) {
+    const int item = p * 4 + g;
+    uint32_t x[4] = {vv[p].x, vv[p].y, vv[p].z, vv[p].w};
+    transpose8x8_h(x, i);
+    const int kb8 = item >> 2, c = item & 3;
+    const int d = c * 8 + i;
+    const int kk = (kb8 * 8) & 63;
+    uint8_t* blk = dvt + ((kb8 * 8) >> 6) * (HD * 128);
+    *reinterpret_cast<uint4*>(blk + d * 128 + (((kk >> 3) ^ (d & 7)) << 4)) = make_uint4(x[0], x[1], x[2], x[3]);
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __half* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V,
                     __half* __restrict__ O, int Lq, int Lk, long q_rs, long k_rs, long v_rs, long o_rs, long q_bs,
@@ -197,24 +238,28 @@ attention_tc_kernel(const __half* __restrict__ Q, const __half* __restrict__ K, 
   fence_proxy_async_smem();
   __syncthreads();
 
-  if (warp == 5) {
-    // ===================== tile loader: runs ahead of the MMAs, bounded by the buffers =====================
+  if (warp >= 5) {
+    // ===================== tile loaders: run ahead of the MMAs, bounded by the buffers =====================
+    // warp 5 takes the odd chunks, warp 6 the even ones: a chunk costs its loader one L2 round trip + 14 shuffle
+    // transposes, which one warp alone cannot hide behind the softmax of a 112-key chunk
     // K(c), c >= 2, into tile c % 3 (free when S(c-3) completed); V^T(c), c >= 1, into tile c & 1 (free when P(c-2).V did)
-    for (int c = 1; c < nchunks + 1; ++c) {
-      if (c < nchunks) {
-        if (c >= 2) mbar_wait(&v_free[c & 1], ((c - 2) >> 1) & 1);
-        load_vt_chunk<1>(sVt + (c & 1) * SVT_BYTES, v, c * KC, Lk, v_rs, 0, lane);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&v_ready[c & 1]);
-      }
+    // chunk c's V^T tile and chunk c+1's K tile are needed at the same time (P(c).V and S(c+1) are issued back to back),
+    // so they are loaded together
+    for (int c = (warp == 5 ? 1 : 2); c < nchunks; c += 2) {
       const int ck = c + 1;
+      if (c >= 2) mbar_wait(&v_free[c & 1], ((c - 2) >> 1) & 1);
       if (ck < nchunks) {
         if (ck >= 3) mbar_wait(&k_free[ck % 3], ((ck - 3) / 3) & 1);
-        load_k_chunk<32>(sK + (ck % 3) * SK_BYTES, k, ck * KC, Lk, k_rs, lane);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&k_ready[ck % 3]);
+        load_kv_chunk_warp(sK + (ck % 3) * SK_BYTES, sVt + (c & 1) * SVT_BYTES, k, v, ck * KC, c * KC, Lk, k_rs, v_rs,
+                           lane);
+      } else {
+        load_vt_chunk<1>(sVt + (c & 1) * SVT_BYTES, v, c * KC, Lk, v_rs, 0, lane);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&v_ready[c & 1]);
+        if (ck < nchunks) mbar_arrive(&k_ready[ck % 3]);
       }
     }
   } else if (warp == 4) {
@@ -275,39 +320,63 @@ attention_tc_kernel(const __half* __restrict__ Q, const __half* __restrict__ K, 
       const int valid = min(KC, Lk - j * KC);
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sraw[KC];
-#pragma unroll
-      for (int c = 0; c < KC / 32; ++c)
-        tmem_ld32(tlane + COL_S + (j & 1) * KC + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]));
-      if (KC % 32 == 16)
-        tmem_ld16(tlane + COL_S + (j & 1) * KC + (KC / 32) * 32,
-                  *reinterpret_cast<uint32_t(*)[16]>(&sraw[(KC / 32) * 32]));
-      tmem_ld_wait();
-      if (valid < KC) {               // last chunk only: keys past Lk never win the max and get probability 0
-#pragma unroll
-        for (int i = 0; i < KC; ++i)
-          if (i >= valid) sraw[i] = 0xff800000u;      // -inf
-      }
+      // two passes over the chunk's scores in TMEM (32-column pieces): the maximum first, then the probabilities -
+      // reading twice is cheaper than holding 112 scores in registers next to 56 packed probabilities
+      const uint32_t scol = tlane + COL_S + (j & 1) * KC;
       float cmax = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < KC; ++i) cmax = fmaxf(cmax, __uint_as_float(sraw[i]));
+      for (int c = 0; c < (KC + 31) / 32; ++c) {
+        uint32_t t[32];
+        if (c * 32 + 32 <= KC) {
+          tmem_ld32(scol + c * 32, t);
+        } else {
+          tmem_ld16(scol + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&t[0]));
+#pragma unroll
+          for (int i = 16; i < 32; ++i) t[i] = 0xff800000u;
+        }
+        tmem_ld_wait();
+        if (valid < KC) {             // last chunk only: keys past Lk never win the max
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) t[i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, __uint_as_float(t[i]));
+      }
       const float m_new = fmaxf(m_run, cmax);
       const float alpha = ex2_approx((m_run - m_new) * scale_log2e);      // ex2(-inf) = 0 on the first chunk
       const float mb = m_new * scale_log2e;
       float rsum = 0.f;
       uint4 pk[KC / 8];
 #pragma unroll
-      for (int c8 = 0; c8 < KC / 8; ++c8) {
-        float p[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          p[e] = ex2_approx(fmaf(__uint_as_float(sraw[c8 * 8 + e]), scale_log2e, -mb));
-          rsum += p[e];
+      for (int c = 0; c < (KC + 31) / 32; ++c) {
+        uint32_t t[32];
+        if (c * 32 + 32 <= KC) {
+          tmem_ld32(scol + c * 32, t);
+        } else {
+          tmem_ld16(scol + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&t[0]));
         }
-        pk[c8].x = pack_half2(p[0], p[1]);
-        pk[c8].y = pack_half2(p[2], p[3]);
-        pk[c8].z = pack_half2(p[4], p[5]);
-        pk[c8].w = pack_half2(p[6], p[7]);
+        tmem_ld_wait();
+        if (valid < KC) {             // ... and get probability 0
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) t[i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          if (c * 32 + q8 * 8 < KC) {
+            float p[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              p[e] = ex2_approx(fmaf(__uint_as_float(t[q8 * 8 + e]), scale_log2e, -mb));
+              rsum += p[e];
+            }
+            pk[c * 4 + q8].x = pack_half2(p[0], p[1]);
+            pk[c * 4 + q8].y = pack_half2(p[2], p[3]);
+            pk[c * 4 + q8].z = pack_half2(p[4], p[5]);
+            pk[c * 4 + q8].w = pack_half2(p[6], p[7]);
+          }
+        }
       }
       l_run = fmaf(l_run, alpha, rsum);
       m_run = m_new;

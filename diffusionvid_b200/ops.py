@@ -180,8 +180,8 @@ def maxpool3x3s2(x):
 
 
 # ------------------------------------------------------------------------------------------------ decoder
-# default: the mma.sync flash kernel.  The tcgen05 kernel (attention_tc.cu) is within 14 % (self, 300 keys: 11.1 vs 9.8 us)
-# / 22 % (cross, 900 keys: 30.9 vs 25.2 us) of it in isolation and costs 1.2 % of the step inside the captured decode unit
+# default: the mma.sync flash kernel.  The tcgen05 kernel (attention_tc.cu) is within 23 % (self, 300 keys: 12.1 vs 9.8 us)
+# / 9 % (cross, 900 keys: 27.6 vs 25.3 us) of it in isolation and costs 1.2 % of the step inside the captured decode unit
 # (profiles/r02_attention_ab.json): with head dim 32 both contractions are tiny (K = 32, N = 32) and the chain
 # S -> TMEM -> softmax -> smem -> P.V -> TMEM of every key chunk is longer than keeping S and P in registers.
 ATTENTION_TC = bool(int(__import__("os").environ.get("DVID_ATTN_TC", "0")))
