@@ -542,14 +542,15 @@ roi_dynconv_kernel(RoiLevels lv, const float* __restrict__ boxes, int boxes_per_
 // M=128 tile whose upper 64 rows read whatever follows the operand in shared memory (the next k-block / the next
 // buffer, always inside the CTA's allocation); rows are independent in a GEMM, TMEM lanes 64..127 are never read.
 // One box per CTA, two CTAs per SM (each allocates 256 TMEM columns), 8 warps: all gather, warp 1 issues the MMAs,
-// warps 0,1,4,5 (TMEM sub-partitions 0 and 1 = lanes 0..63) run the two LayerNorm epilogues, all store.
+// warps 0,1,4,5 (TMEM sub-partitions 0 and 1 = lanes 0..63) run the LayerNorm(64) epilogue, all eight the LayerNorm(256)
+// one (bmm2 is issued as two N=128 halves, the second into lanes 64..127), all store.
 constexpr int TC_ROI = 0;                       // 4 x 8 KB; reused as the [64][512 B] output staging tile
 constexpr int TC_P1 = TC_ROI + 4 * 8192;        // 4 x 8 KB
 constexpr int TC_F1 = TC_P1 + 4 * 8192;         // 8 KB
 constexpr int TC_P2 = TC_F1 + 8192;             // 32 KB (also the don't-care rows of the F1 operand)
 constexpr int TC_LN = TC_P2 + 32768;            // gamma2 | beta2 (256 floats each)
-constexpr int TC_STAT = TC_LN + 2 * 256 * 4;    // [2 halves][64 rows] float2
-constexpr int TC_BAR = TC_STAT + 2 * 64 * 8;    // mbarriers + tmem slot
+constexpr int TC_STAT = TC_LN + 2 * 256 * 4;    // [4 column quarters][64 rows] float2
+constexpr int TC_BAR = TC_STAT + 4 * 64 * 8;    // mbarriers + tmem slot
 constexpr int TC_TOTAL = TC_BAR + 64 + 1024;    // + alignment slack
 
 struct DynMaps {
@@ -698,66 +699,73 @@ roi_dynconv_tc_kernel(const __grid_constant__ DynMaps maps, RoiLevels lv, const 
     mbar_wait(p2_full, 0);
     tc_fence_after();
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc_f16(128, D);
-      const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(sF1));
-      const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(sP2));
+      // two N=128 halves. The second one reads the F1 tile through a view that starts 8 KB earlier, so its 64 real rows
+      // are rows 64..127 of the M=128 tile and land in TMEM lanes 64..127: all four sub-partitions hold one half of
+      // the output and all eight warps share the LayerNorm(256) epilogue.
+      const uint32_t idesc = umma_idesc_f16(128, D / 2);
+      const uint64_t adesc0 = umma_desc_sw128_kmajor(smem_u32(sF1));
+      const uint64_t bdesc0 = umma_desc_sw128_kmajor(smem_u32(sP2));
+      const uint64_t adesc1 = umma_desc_sw128_kmajor(smem_u32(sF1 - 8192));
+      const uint64_t bdesc1 = umma_desc_sw128_kmajor(smem_u32(sP2 + 128 * 128));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, k ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 128, adesc1 + 2 * k, bdesc1 + 2 * k, idesc, k ? 1u : 0u);
       umma_commit(mma_bar);
     }
     __syncwarp();
   }
-  if (epi) {
+  {
     // ===================== LayerNorm(256) + ReLU -> staging tile (the ROI buffer, plain swizzled rows) =====================
+    // warp w: sub-partition q = w % 4 -> output columns 128*(q/2) .. +127 of rows 32*(q%2) .. +31; 64-column part w / 4.
+    if (!epi) mbar_wait(mma_bar, 0);
     mbar_wait(mma_bar, 1);
     tc_fence_after();
-    const uint32_t tcol = tlane + half * 128;
+    const int side = q >> 1, part = warp >> 2;
+    const int row = (q & 1) * 32 + lane;
+    const int col0 = side * 128 + part * 64;
+    uint32_t v[2][32];
+    tmem_ld32(tlane + col0, v[0]);
+    tmem_ld32(tlane + col0 + 32, v[1]);
+    tmem_ld_wait();
     float sum = 0.f, sq = 0.f;
 #pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      uint32_t v0[32], v1[32];
-      tmem_ld32(tcol + c2 * 64, v0);
-      tmem_ld32(tcol + c2 * 64 + 32, v1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float a = __uint_as_float(v0[j]), c = __uint_as_float(v1[j]);
-        sum += a + c;
-        sq = fmaf(a, a, sq);
-        sq = fmaf(c, c, sq);
-      }
+    for (int j = 0; j < 32; ++j) {
+      const float a = __uint_as_float(v[0][j]), c = __uint_as_float(v[1][j]);
+      sum += a + c;
+      sq = fmaf(a, a, sq);
+      sq = fmaf(c, c, sq);
     }
-    sStat[half * 64 + r] = make_float2(sum, sq);
-    named_bar_sync(1, 128);
-    const float2 other = sStat[(half ^ 1) * 64 + r];
-    const float mean = (sum + other.x) * (1.f / D);
-    const float rstd = rsqrtf(fmaxf((sq + other.y) * (1.f / D) - mean * mean, 0.f) + 1e-5f);
+    sStat[(side * 2 + part) * 64 + row] = make_float2(sum, sq);
+    __syncthreads();
+    float tsum = 0.f, tsq = 0.f;
 #pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      uint32_t vv[2][32];
-      tmem_ld32(tcol + c2 * 64, vv[0]);
-      tmem_ld32(tcol + c2 * 64 + 32, vv[1]);
-      tmem_ld_wait();
+    for (int i = 0; i < 4; ++i) {
+      const float2 o = sStat[i * 64 + row];
+      tsum += o.x;
+      tsq += o.y;
+    }
+    const float mean = tsum * (1.f / D);
+    const float rstd = rsqrtf(fmaxf(tsq * (1.f / D) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const int col = half * 128 + c2 * 64 + h * 32 + c4 * 8;
-          const float4 ga = *reinterpret_cast<const float4*>(sG2 + col), gb = *reinterpret_cast<const float4*>(sG2 + col + 4);
-          const float4 ba = *reinterpret_cast<const float4*>(sB2 + col), bb = *reinterpret_cast<const float4*>(sB2 + col + 4);
-          const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-          const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-          float y[8];
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int col = col0 + h * 32 + c4 * 8;
+        const float4 ga = *reinterpret_cast<const float4*>(sG2 + col), gb = *reinterpret_cast<const float4*>(sG2 + col + 4);
+        const float4 ba = *reinterpret_cast<const float4*>(sB2 + col), bb = *reinterpret_cast<const float4*>(sB2 + col + 4);
+        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        float y[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            y[e] = fmaxf((__uint_as_float(vv[h][c4 * 8 + e]) - mean) * rstd * gg[e] + be[e], 0.f);
-          uint4 pk;
-          pk.x = pack_half2(y[0], y[1]);
-          pk.y = pack_half2(y[2], y[3]);
-          pk.z = pack_half2(y[4], y[5]);
-          pk.w = pack_half2(y[6], y[7]);
-          *reinterpret_cast<uint4*>(sRoi + off512(r, col >> 3)) = pk;
-        }
+        for (int e = 0; e < 8; ++e)
+          y[e] = fmaxf((__uint_as_float(v[h][c4 * 8 + e]) - mean) * rstd * gg[e] + be[e], 0.f);
+        uint4 pk;
+        pk.x = pack_half2(y[0], y[1]);
+        pk.y = pack_half2(y[2], y[3]);
+        pk.z = pack_half2(y[4], y[5]);
+        pk.w = pack_half2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(sRoi + off512(row, col >> 3)) = pk;
       }
     }
     tc_fence_before();

@@ -138,10 +138,17 @@ class DiffusionDet(nn.Module):
         self.fused_rows = bool(int(_os.environ.get("DVID_FUSED_ROWS", hp.get("fused_rows", 0))))
         # DynamicConv bmm pair on tcgen05 (roi_dynconv_tc_kernel) or on mma.sync (roi_dynconv_kernel).  Both kernels take
         # 145 us per 2400 boxes in isolation - they are bound by the fp32 bilinear gather on the CUDA cores, not by the
-        # contractions (profiles/r02_ncu_dynconv_warm.txt) - but inside the pipeline the tcgen05 variant costs 1.7 % of
-        # the step (4 % with the decode overlapping the next backbone pass: 806 vs 838 frames/s): only the four warps
-        # that own TMEM lanes 0..63 can run its LayerNorm epilogues.  Default: mma.sync; DVID_DYNCONV_TC=1 selects tcgen05.
+        # contractions (profiles/r02_ncu_dynconv_warm.txt).  Alone the tcgen05 variant is the faster one (135 vs 145 us
+        # per call at 2400 boxes, tools/bench_dynconv_ab.py) since bmm2 is issued as two N=128 halves over all 128 TMEM
+        # lanes and all eight warps share the LayerNorm(256) epilogue; inside the pipeline, with the decode overlapping
+        # the next backbone pass, it is 0.8 % behind (837 vs 844 frames/s, run-to-run noise is +-1 %): its 107 KB of
+        # shared memory per CTA leave less room for the co-resident conv CTAs.  Default: mma.sync; DVID_DYNCONV_TC=1
+        # selects tcgen05.
         self.dynconv_tc = bool(int(_os.environ.get("DVID_DYNCONV_TC", hp.get("dynconv_tc", 0))))
+        # The global cross-attention (2400 queries x 900 memory rows, once per DDIM step) on the tcgen05 kernel: 27.6 vs
+        # 25.3 us alone, 842.6 vs 844.4 frames/s in the step (noise).  Both attentions stay on the warp-level kernel
+        # unless DVID_CROSS_ATTN_TC=1 / DVID_ATTN_TC=1.
+        self.cross_attn_tc = bool(int(_os.environ.get("DVID_CROSS_ATTN_TC", hp.get("cross_attn_tc", 0))))
         self.extract_batch = int(_os.environ.get("DVID_EXTRACT_BATCH", hp.get("extract_batch", 32)))
         self.dyn_chunk_frames = int(_os.environ.get("DVID_DYN_CHUNK", hp.get("dyn_chunk_frames", 0)))
         # frames that arrive in HOST memory: run the backbone on the frames already uploaded while the later ones are
@@ -544,7 +551,8 @@ class DiffusionDet(nn.Module):
         q = ops.gemm(obj16, ga["q_w"], ga["q_b"])
         kv = self._mem_kv if kv is None else kv
         ctx = torch.empty((M, 256), device=dev, dtype=H)
-        ops.attention(q, kv, kv[:, 256:], ctx, 1, 8, M, kv.shape[0], 256, 512, 512, 256, 0, 0, 0, 0)
+        ops.attention(q, kv, kv[:, 256:], ctx, 1, 8, M, kv.shape[0], 256, 512, 512, 256, 0, 0, 0, 0,
+                      tc=True if self.cross_attn_tc else None)
         cond16 = torch.empty((M, 256), device=dev, dtype=H)
         if self.fused_rows:
             ops.gemm_row(ctx, ga["o_w"], bias=ga["o_b"], act=2, out_f16=cond16)
