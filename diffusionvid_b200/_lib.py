@@ -49,6 +49,7 @@ SIGNATURES = {
     "dvid_cdist_f32": [P, P, I, I, P],
     "dvid_furthest_point_sampling": [I, I, I, P, P, P, P],
     "dvid_roi_align_legacy_forward": [P, P, I, I, I, I, F, I, I, I, P, P],
+    "dvid_vid_match": [P, P, P, P, P, P, P, P, I, F, ctypes.c_double, P, P, P, P],
     "dvid_swin_rows": [P, I, P, I, P, P, P, P, I, I, I, I, I, I, P],
     "dvid_swin_patch_merge": [P, I, I, I, I, P, P, P, P],
     "dvid_swin_patch_gather": [P, P, I, I, I, P, P, P],

@@ -2,7 +2,7 @@
 #include "../../include/dvid_b200.h"
 #include "dvid_internal.h"
 
-#define DVID_ABI_VERSION 15
+#define DVID_ABI_VERSION 16
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
@@ -48,6 +48,15 @@ int dvid_roi_align_legacy_forward(const float* input, const float* rois, int num
   if (num_rois > 0 && (!input || !rois || !out)) return DVID_ERR_ARG;
   return dvid::roi_align_legacy_launch(input, rois, num_rois, channels, height, width, spatial_scale, pooled_height,
                                        pooled_width, sampling_ratio, out, S(stream));
+}
+
+int dvid_vid_match(const float* pred_boxes, const int* pred_labels, const int* order, const int* pred_off,
+                   const float* gt_boxes, const int* gt_labels, const unsigned char* gt_ignore, const int* gt_off,
+                   int n_images, float iou_thresh, double empty_weight, unsigned char* gt_taken, unsigned char* hit,
+                   double* weight, void* stream) {
+  if (n_images > 0 && (!pred_off || !gt_off || !hit || !weight)) return DVID_ERR_ARG;   // the packed arrays may be empty
+  return dvid::vid_match_launch(pred_boxes, pred_labels, order, pred_off, gt_boxes, gt_labels, gt_ignore, gt_off,
+                                n_images, iou_thresh, empty_weight, gt_taken, hit, weight, S(stream));
 }
 
 int dvid_conv_streamk(int enable) { return dvid::conv_streamk_enable(enable); }

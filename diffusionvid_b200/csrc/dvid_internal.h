@@ -86,6 +86,11 @@ int fps_launch(int b, int n, int m, const float* dist, float* temp, int* idx, cu
 int roi_align_legacy_launch(const float* in, const float* rois, int num_rois, int C, int H, int W, float scale, int PH,
                             int PW, int sampling_ratio, float* out, cudaStream_t stream);
 
+int vid_match_launch(const float* pred_boxes, const int* pred_labels, const int* order, const int* pred_off,
+                     const float* gt_boxes, const int* gt_labels, const unsigned char* gt_ignore, const int* gt_off,
+                     int n_images, float thr, double empty_weight, unsigned char* gt_taken, unsigned char* hit,
+                     double* weight, cudaStream_t stream);
+
 int head_tail_launch(const void* fc, const void* cls_w, const float* cls_g, const float* cls_b, const void* logit_w,
                      const float* logit_bias, int C, const void* const* reg_w, const float* const* reg_g,
                      const float* const* reg_b, const void* delta_w, const float* delta_bias, const float* boxes_in,

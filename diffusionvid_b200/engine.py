@@ -140,5 +140,7 @@ def inference(model, data_loader, device="cuda", output_folder=None, timer=None,
         save_predictions(predictions, output_folder)
     if evaluate:
         from . import evaluation
-        return predictions, evaluation.do_vid_evaluation(data_loader.dataset, predictions, output_folder, logger)
+        # matching on the GPU (one dvid_vid_match launch over all frames) when the model ran on one
+        return predictions, evaluation.do_vid_evaluation(data_loader.dataset, predictions, output_folder, logger,
+                                                         device=device if device.type == "cuda" else "cpu")
     return predictions

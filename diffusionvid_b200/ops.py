@@ -513,7 +513,7 @@ def roi_align_legacy_forward(inp, rois, spatial_scale, pooled_height, pooled_wid
     (n,C,ph,pw) fp32, maskrcnn-benchmark semantics (no half-pixel shift, roi size >= 1)."""
     _chk(inp, F32, "input"); _chk(rois, F32, "rois")
     if inp.dim() != 4 or rois.dim() != 2 or rois.shape[1] != 5:
-        raise DvidError("roi_align_forward: input (N,C,H,W), rois (n,5)")
+        raise _lib.DvidError("roi_align_forward: input (N,C,H,W), rois (n,5)")
     n = rois.shape[0]
     N, C, Hh, Ww = inp.shape
     out = torch.empty((n, C, int(pooled_height), int(pooled_width)), device=inp.device, dtype=F32)
@@ -522,6 +522,32 @@ def roi_align_legacy_forward(inp, rois, spatial_scale, pooled_height, pooled_wid
                                                    ptr(out), cur_stream()), "dvid_roi_align_legacy_forward")
     _cnt()
     return out
+
+
+def vid_match(pred_boxes, pred_labels, order, pred_off, gt_boxes, gt_labels, gt_ignore, gt_off, iou_thresh,
+              empty_weight):
+    """vid_eval.py:167-291 greedy matching of all images in one launch (dvid_vid_match).  Packed device tensors: boxes
+    fp32 [n,4], labels int32, offsets int32 [images+1], order int32 (per image, descending score), gt_ignore uint8.
+    Returns (hit uint8 [Np], weight fp64 [Np]) indexed by position in `order`."""
+    _chk(pred_boxes, F32, "pred_boxes"); _chk(gt_boxes, F32, "gt_boxes")
+    for t, n in ((pred_labels, "pred_labels"), (order, "order"), (pred_off, "pred_off"), (gt_labels, "gt_labels"),
+                 (gt_off, "gt_off")):
+        _chk(t, torch.int32, n)
+    _chk(gt_ignore, torch.uint8, "gt_ignore")
+    n_img = pred_off.numel() - 1
+    if gt_off.numel() != n_img + 1 or order.numel() != pred_labels.numel() or pred_boxes.shape[0] != order.numel() \
+            or gt_boxes.shape[0] != gt_labels.numel() or gt_ignore.numel() != gt_labels.numel():
+        raise _lib.DvidError("vid_match: inconsistent packed sizes")
+    dev = pred_boxes.device
+    taken = torch.zeros(max(gt_labels.numel(), 1), device=dev, dtype=torch.uint8)
+    hit = torch.empty(max(order.numel(), 1), device=dev, dtype=torch.uint8)
+    weight = torch.empty(max(order.numel(), 1), device=dev, dtype=torch.float64)
+    check(_lib.lib().dvid_vid_match(ptr(pred_boxes), ptr(pred_labels), ptr(order), ptr(pred_off), ptr(gt_boxes),
+                                    ptr(gt_labels), ptr(gt_ignore), ptr(gt_off), n_img, float(iou_thresh),
+                                    float(empty_weight), ptr(taken), ptr(hit), ptr(weight), cur_stream()),
+          "dvid_vid_match")
+    _cnt()
+    return hit[:order.numel()], weight[:order.numel()]
 
 
 def decode_jpeg(data, device="cuda"):

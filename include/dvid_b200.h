@@ -228,6 +228,22 @@ DVID_API int dvid_roi_align_legacy_forward(const float* input, const float* rois
                                            int pooled_width, int sampling_ratio, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * ImageNet-VID evaluator, csrc/vid_match.cu.
+ */
+/* The greedy matching of mega_core/data/datasets/evaluation/vid/vid_eval.py:167-291 (calc_detection_vid_prec_rec,
+ * incl. the motion-specific "ignored ground truth" rules :233-264) for ALL images in one launch.  Packed inputs:
+ * pred_boxes [Np][4] fp32 xyxy, pred_labels [Np], pred_off [n_images+1] (image i owns detections pred_off[i] ..
+ * pred_off[i+1]-1), order [Np] = detection indices, image by image, each image in descending score order (stable);
+ * gt_boxes [Ng][4], gt_labels [Ng], gt_ignore [Ng] (1 = outside the motion range), gt_off [n_images+1];
+ * gt_taken [Ng] zero-initialised scratch.  Outputs, indexed by POSITION in `order`: hit [Np] (1 = matched) and
+ * weight [Np] fp64 = the reference's pred_ignore (0 regular, 1 dropped, fraction = partial false positive;
+ * empty_weight for a detection whose class has no ground truth in the image). */
+DVID_API int dvid_vid_match(const float* pred_boxes, const int* pred_labels, const int* order, const int* pred_off,
+                            const float* gt_boxes, const int* gt_labels, const unsigned char* gt_ignore,
+                            const int* gt_off, int n_images, float iou_thresh, double empty_weight,
+                            unsigned char* gt_taken, unsigned char* hit, double* weight, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Swin Transformer backbone (mega_core/modeling/backbone/swintransformer.py), csrc/swin.cu.  The linear layers
  * (qkv / proj / fc1+GELU / fc2 / reduction / patch-embed projection) are dvid_gemm_f16 calls.
  */
