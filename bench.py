@@ -428,6 +428,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback "
                          "(use --impl reference for the CPU oracle arm)")
     torch.cuda.set_device(local)
+    if int(os.environ.get("DVID_MAIN_PRIORITY", "0")) != 0:     # experiment: the caller's (backbone) stream above the decode streams
+        torch.cuda.set_stream(torch.cuda.Stream(priority=int(os.environ["DVID_MAIN_PRIORITY"])))
     dev = torch.device("cuda", local)
     if dist:
         torch.distributed.init_process_group("nccl", device_id=dev)

@@ -148,6 +148,7 @@ class DiffusionDet(nn.Module):
         # The global cross-attention (2400 queries x 900 memory rows, once per DDIM step) on the tcgen05 kernel: 27.6 vs
         # 25.3 us alone, 842.6 vs 844.4 frames/s in the step (noise).  Both attentions stay on the warp-level kernel
         # unless DVID_CROSS_ATTN_TC=1 / DVID_ATTN_TC=1.
+        self.decode_priority = int(_os.environ.get("DVID_DECODE_PRIORITY", hp.get("decode_priority", 0)))
         self.cross_attn_tc = bool(int(_os.environ.get("DVID_CROSS_ATTN_TC", hp.get("cross_attn_tc", 0))))
         self.extract_batch = int(_os.environ.get("DVID_EXTRACT_BATCH", hp.get("extract_batch", 32)))
         self.dyn_chunk_frames = int(_os.environ.get("DVID_DYN_CHUNK", hp.get("dyn_chunk_frames", 0)))
@@ -805,7 +806,8 @@ class DiffusionDet(nn.Module):
         if dev.type == "cuda":
             ops.conv_streamk(self.streamk)       # process-wide library switch: set per call (several models may coexist)
             if self.overlap_decode and self._decode_stream is None:
-                self._decode_stream = [torch.cuda.Stream() for _ in range(self.decode_streams)]
+                self._decode_stream = [torch.cuda.Stream(priority=self.decode_priority)
+                                       for _ in range(self.decode_streams)]
         N = self.num_proposals
         ib = self.infer_batch
         if infos["frame_category"] == 0:
