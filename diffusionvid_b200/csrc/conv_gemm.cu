@@ -78,6 +78,8 @@ struct ConvGemmParams {
   float* sk_ws;
   unsigned* sk_flags;
   FastDiv div_total_kb;
+  // PATCH variants (3x3 / stride 1): bytes of one A patch ((th + 2) rows x tw pixels x 128 B) and of one patch row
+  int patch_bytes, patch_row_bytes;
 };
 
 // BSTAT ("B-stationary", K <= 256): the whole [BN x K] weight tile stays resident in smem while the CTA walks a
@@ -105,17 +107,37 @@ constexpr int IDENT_BYTES = 16 * 128;   // 16 rows (n) x 64 k fp16, 128-byte swi
 // CTAs are dispatched in index order and are co-resident (1 per SM, grid <= SMs): no deadlock, and both sides of the
 // hand-off overlap a main loop (the first version parked tails and finished heads as each CTA's LAST item: the
 // exposed wait + 128 KB read cost as much as the saved second wave).
-template <int BN, bool BSTAT = false, bool RES = false>
+// PATCH ("column patch", 3x3 stride-1 convolutions): the three taps of one filter COLUMN read the same pixels shifted by
+// whole image rows, so one TMA box of (th + 2) rows x tw pixels serves three k-blocks - tap (dy, dx) is the view that
+// starts dy rows (dy * tw * 128 B, a multiple of the 1024-byte swizzle atom for tw >= 8) into the patch of column dx.
+// The A operand then crosses L2->SM 3 * (th + 2) / th times per channel block instead of 9 times (th = 8: 3.75), which
+// is what bounds the main loop of these layers (a 64-wide tile costs 0.55 of a 256-wide one: bytes per k-block, not
+// MMA time).  A patches and B tiles ride separate rings (PA x 24 KB, PB x B_STAGE_BYTES); the k-blocks of a tile are
+// visited column by column: (dx, channel block, dy).
+constexpr int A_PATCH_BYTES = 24 * 1024;   // (th + 2) * tw * 128 <= 24 KB: (th, tw) in {(4,32), (8,16), (16,8)}
+
+// CTA2 ("CTA pair", BN = 256 plain convolutions): the two CTAs of a {2,1,1} cluster compute two adjacent M tiles with ONE
+// tcgen05.mma.cta_group::2 of M = 256 per k-step.  Each CTA loads its own A tile (16 KB per k-block) and only HALF of the
+// B tile (16 KB instead of 32 KB): what bounds these layers is the bytes an SM can take in per k-block (measured: every
+// tile width runs at ~90 GB/s per SM), so 32 KB instead of 48 KB per k-block and a six-deep ring instead of four.
+template <int BN, bool BSTAT = false, bool RES = false, bool PATCH = false, bool CTA2 = false>
 struct ConvGemmCfg {
-  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGES0 = BSTAT ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8));
+  static constexpr int B_STAGE_BYTES = (CTA2 ? BN / 2 : BN) * BLOCK_K * 2;
+  static constexpr int STAGES0 = CTA2 ? 6 : (BSTAT ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8)));
   static constexpr int STAGES = STAGES0 - (RES ? 1 : 0);   // room for the identity tile (and keeps BN=256 under 227 KB)
+  static constexpr int PA = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);   // A patch stages
+  static constexpr int PB = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);   // B tile stages
+  static constexpr int NBAR = PATCH ? (PA + PB) : STAGES;              // full / empty barrier pairs of the rings
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int RING_BYTES =
-      BSTAT ? (STAGES * A_STAGE_BYTES + BSTAT_MAX_KB * B_STAGE_BYTES) : (STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+      PATCH ? (PA * A_PATCH_BYTES + PB * B_STAGE_BYTES)
+            : (BSTAT ? (STAGES * A_STAGE_BYTES + BSTAT_MAX_KB * B_STAGE_BYTES) : (STAGES * (A_STAGE_BYTES + B_STAGE_BYTES)));
   static constexpr int SMEM_BYTES = RING_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
                                     (BN * 4 > 512 ? BN * 4 : 512) /*bias staging: each epilogue group its own half*/ +
                                     (RES ? IDENT_BYTES : 0);
+  static_assert(!PATCH || (!BSTAT && !RES), "the column-patch walk serves the plain variants only");
+  static_assert(!CTA2 || (!BSTAT && !RES && !PATCH && BN == 256), "CTA pairs serve the plain 256-wide variant only");
+  static_assert(2 * NBAR * 8 + 6 * 8 + 4 <= 256, "barrier block");
 };
 
 // GELU, erf form (torch.nn.GELU default; Swin MLP, swintransformer.py:47-66): x * Phi(x).  erff() costs ~30
@@ -155,25 +177,31 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
 }
 constexpr int BAR_SK = 8;   // named barrier of the eight epilogue warps (stream-K hand-off)
 
-template <int BN, bool BSTAT, bool RES, bool SK>
+template <int BN, bool BSTAT, bool RES, bool SK, bool PATCH = false, bool CTA2 = false>
 __global__ void __launch_bounds__(384, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BN, BSTAT, RES>;
+  using Cfg = ConvGemmCfg<BN, BSTAT, RES, PATCH, CTA2>;
+  static_assert(!CTA2 || !SK, "no stream-K for CTA pairs");
+  const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs of the pair)
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NBAR = Cfg::NBAR;
+  constexpr int PA = Cfg::PA, PB = Cfg::PB;
+  static_assert(!PATCH || !SK, "no stream-K in the column-patch walk");
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B (128-byte swizzle atoms) with pointer arithmetic on the __shared__ symbol, so the compiler keeps
   // the shared state space (LDS/STS instead of generic LD/ST in the epilogue)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + STAGES * A_STAGE_BYTES;      // ring (normal) or the resident [kb][BN x 64] weight tile (BSTAT)
+  // B: ring (normal / PATCH) or the resident [kb][BN x 64] weight tile (BSTAT)
+  uint8_t* sB = sA + (PATCH ? PA * A_PATCH_BYTES : STAGES * A_STAGE_BYTES);
   uint8_t* sOut = smem + Cfg::RING_BYTES;
   uint8_t* sIdent = sOut + 2 * OUT_STAGE_BYTES;   // RES: 16x16 identity B tile (1024-byte aligned for the 128B swizzle)
   uint8_t* sCtl = sIdent + (RES ? IDENT_BYTES : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sCtl);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + NBAR;          // PATCH: [0, PA) = A patch ring, [PA, PA + PB) = B ring
+  uint64_t* tmem_full = empty_bar + NBAR;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* bres_full = tmem_empty + 2;           // BSTAT: resident weights landed / may be overwritten
   uint64_t* bres_empty = bres_full + 1;
@@ -190,19 +218,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NBAR; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], CTA2 ? 16 : 8);  // one arrive per epilogue warp (CTA2: of both CTAs, on the leader's)
     }
     mbar_init(bres_full, 1);
     mbar_init(bres_empty, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (CTA2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   if (warp == 3 && p.w_slice_bytes != 0 && elect_one()) {
     const unsigned long long off = static_cast<unsigned long long>(blockIdx.x) * p.w_slice_bytes;
     if (off < p.w_bytes) {
@@ -228,21 +259,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_proxy_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  // CTA2: the pair walks PAIRS of adjacent M tiles (an odd tail tile is paired with an out-of-range one: its loads are
+  // zero-filled and its stores clipped by TMA)
+  const int total_tiles = CTA2 ? ((p.m_tiles + 1) >> 1) * p.n_tiles : p.m_tiles * p.n_tiles * p.splits;
   const int tw = 1 << p.tw_log2;
   // tile walk: normal = strided over the grid, n fastest; BSTAT = one contiguous range per CTA, m fastest (splits == 1)
   const int tile_begin = BSTAT ? static_cast<int>(static_cast<long long>(total_tiles) * blockIdx.x / gridDim.x)
-                               : static_cast<int>(blockIdx.x);
+                               : static_cast<int>(CTA2 ? (blockIdx.x >> 1) : blockIdx.x);
   const int tile_end = BSTAT ? static_cast<int>(static_cast<long long>(total_tiles) * (blockIdx.x + 1) / gridDim.x)
                              : total_tiles;
-  const int tile_step = BSTAT ? 1 : static_cast<int>(gridDim.x);
+  const int tile_step = BSTAT ? 1 : static_cast<int>(CTA2 ? (gridDim.x >> 1) : gridDim.x);
   auto decode = [&](int tile, int& n_idx, int& m_idx, int& split) {
     if (BSTAT) {
       p.div_m_tiles.divmod(tile, n_idx, m_idx);
+      split = 0;
+    } else if (CTA2) {
+      int pair;
+      p.div_n_tiles.divmod(tile, pair, n_idx);
+      m_idx = 2 * pair + rank;
       split = 0;
     } else {
       int rest;
@@ -330,6 +369,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
+      int pstage = 0;            // PATCH: A patch ring position (stage / phase walk the B ring)
+      uint32_t pphase = 0;
       int cur_n = pre_n;
       uint32_t bphase = 0;
       int tn = 0;
@@ -355,6 +396,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (++cblk == p.kb_per_tap) { cblk = 0; ++tap; }
           }
         }
+        if (PATCH) {
+          // column by column: one patch of (th + 2) rows per (dx, channel block), then the three weight tiles of its taps
+          for (int dx = 0; dx < 3; ++dx) {
+            for (int cb = 0; cb < p.kb_per_tap; ++cb) {
+              mbar_wait(&empty_bar[pstage], pphase ^ 1);
+              mbar_expect_tx(&full_bar[pstage], p.patch_bytes);
+              tma_load_4d(sA + pstage * A_PATCH_BYTES, &tmA, &full_bar[pstage], cb * BLOCK_K, x_in0 + dx, y_in0, img);
+              if (++pstage == PA) { pstage = 0; pphase ^= 1; }
+              for (int dy = 0; dy < 3; ++dy) {
+                mbar_wait(&empty_bar[PA + stage], phase ^ 1);
+                mbar_expect_tx(&full_bar[PA + stage], Cfg::B_STAGE_BYTES);
+                tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[PA + stage],
+                            (dy * 3 + dx) * p.cin + cb * BLOCK_K, n_idx * BN);
+                if (++stage == PB) { stage = 0; phase ^= 1; }
+              }
+            }
+          }
+          continue;
+        }
         // (tap, channel block, filter row, filter column) of the k-block, advanced incrementally: the divisions
         // they replace were a dependent ~70-instruction chain per k-block on the single producer thread
         int tap = 0, cblk = 0, r = 0, s = 0;
@@ -367,11 +427,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           trace_ev(p, 0, tn, (tile << 8) | kb);     // slot free, load issued
-          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (BSTAT ? 0 : Cfg::B_STAGE_BYTES));
-          tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cblk * BLOCK_K, x_in0 + s, y_in0 + r, img);
-          if (!BSTAT)
-            tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], tap * p.cin + cblk * BLOCK_K,
-                        n_idx * BN);
+          if (CTA2) {
+            // the leader's barrier counts the bytes of both CTAs; each CTA brings its own A rows and half of the B rows
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+            tma_load_4d_pair(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cblk * BLOCK_K, x_in0 + s, y_in0 + r,
+                             img);
+            tma_load_2d_pair(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], tap * p.cin + cblk * BLOCK_K,
+                             n_idx * BN + rank * (BN / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + (BSTAT ? 0 : Cfg::B_STAGE_BYTES));
+            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cblk * BLOCK_K, x_in0 + s, y_in0 + r, img);
+            if (!BSTAT)
+              tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], tap * p.cin + cblk * BLOCK_K,
+                          n_idx * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (++cblk == p.kb_per_tap) {
             cblk = 0;
@@ -391,11 +460,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BN);
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (CTA2: of the leader CTA, for the pair) =====================
+    constexpr uint32_t idesc = umma_idesc_f16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BN);
     int stage = 0;
     uint32_t phase = 0;
+    int pstage = 0;              // PATCH: A patch ring position (stage / phase walk the B ring)
+    uint32_t pphase = 0;
     int as = 0;
     uint32_t aphase = 0;
     int cur_n = -1;
@@ -421,6 +492,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (lane == 0) trace_ev(p, 1, tn, (tile << 8) | 0xff);   // accumulator stage free
       const uint32_t d_tmem = tmem_base + as * BN;
+      if (PATCH) {
+        bool first = true;
+        for (int dx = 0; dx < 3; ++dx) {
+          for (int cb = 0; cb < p.kb_per_tap; ++cb) {
+            mbar_wait(&full_bar[pstage], pphase);
+            for (int dy = 0; dy < 3; ++dy) {
+              mbar_wait(&full_bar[PA + stage], phase);
+              tc_fence_after();
+              if (elect_one()) {
+                // tap (dy, dx): the same patch, dy image rows further down (a whole number of swizzle atoms)
+                const uint64_t adesc =
+                    umma_desc_sw128_kmajor(smem_u32(sA + pstage * A_PATCH_BYTES + dy * p.patch_row_bytes));
+                const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k)
+                  umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+                umma_commit(&empty_bar[PA + stage]);
+                if (dy == 2) {
+                  umma_commit(&empty_bar[pstage]);
+                  if (dx == 2 && cb == p.kb_per_tap - 1) umma_commit(&tmem_full[as]);
+                }
+              }
+              __syncwarp();
+              first = false;
+              if (++stage == PB) { stage = 0; phase ^= 1; }
+            }
+            if (++pstage == PA) { pstage = 0; pphase ^= 1; }
+          }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        continue;
+      }
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -429,15 +532,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(sA + stage * A_STAGE_BYTES));
           const uint64_t bdesc =
               umma_desc_sw128_kmajor(smem_u32(sB + (BSTAT ? kb : stage) * Cfg::B_STAGE_BYTES));
+          if (CTA2) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (kb == kb_end - 1) {
-            if (!RES) umma_commit(&tmem_full[as]);
-            if (last_of_n) umma_commit(bres_empty);
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);              // the slot is free in both CTAs
+            if (kb == kb_end - 1) umma_commit_pair(&tmem_full[as]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in 16-byte units
+              umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb_end - 1) {
+              if (!RES) umma_commit(&tmem_full[as]);
+              if (last_of_n) umma_commit(bres_empty);
+            }
           }
         }
         __syncwarp();
@@ -725,16 +836,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_leader(&tmem_empty[as]);     // the leader's MMA warp waits for both CTAs' epilogues
+        else mbar_arrive(&tmem_empty[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();      // nothing of the pair is in flight towards either CTA any more
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (CTA2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -827,13 +943,44 @@ int conv_streamk_enable(int on) {
   return 0;
 }
 
-template <int BN, bool BSTAT, bool RES, bool SK = false>
-static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
-                      const ConvGemmParams& p, cudaStream_t stream) {
-  using Cfg = ConvGemmCfg<BN, BSTAT, RES>;
+// CTA-pair variant: {2,1,1} clusters, one pair per TPC, the pairs walk pairs of M tiles
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = ConvGemmCfg<256, false, false, false, true>;
+  auto kernel = conv_gemm_kernel<256, false, false, false, false, true>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, BSTAT, RES, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      return DVID_ERR_CUDA;
+    attr_set = true;
+  }
+  const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmC, tmC, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
+}
+
+template <int BN, bool BSTAT, bool RES, bool SK = false, bool PATCH = false>
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                      const ConvGemmParams& p, cudaStream_t stream) {
+  using Cfg = ConvGemmCfg<BN, BSTAT, RES, PATCH>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, BSTAT, RES, SK, PATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return DVID_ERR_CUDA;
     attr_set = true;
@@ -845,7 +992,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     const size_t bytes = 3 * 2048 * sizeof(unsigned long long);
     cudaMalloc(&q.trace, bytes);
     cudaMemsetAsync(q.trace, 0, bytes, stream);
-    launch_pdl(conv_gemm_kernel<BN, BSTAT, RES, SK>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, q);
+    launch_pdl(conv_gemm_kernel<BN, BSTAT, RES, SK, PATCH>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, q);
     cudaStreamSynchronize(stream);
     static unsigned long long host[3 * 2048];
     cudaMemcpy(host, q.trace, bytes, cudaMemcpyDeviceToHost);
@@ -863,7 +1010,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
       }
     return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
   }
-  launch_pdl(conv_gemm_kernel<BN, BSTAT, RES, SK>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, p);
+  launch_pdl(conv_gemm_kernel<BN, BSTAT, RES, SK, PATCH>, dim3(grid), dim3(384), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, tmR, p);
   return cudaGetLastError() == cudaSuccess ? 0 : DVID_ERR_CUDA;
 }
 
@@ -893,6 +1040,23 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     if (best_tiles < 0 || t < best_tiles) { best_tiles = t; best_log2 = l2; }
   }
   if (best_tiles < 0) return DVID_ERR_SHAPE;
+  // column-patch walk (see ConvGemmCfg): plain 3x3 / stride 1 / pad 1 convolutions.  The tile must be >= 4 rows tall for
+  // the shared patch to pay and >= 8 pixels wide for the row views to stay swizzle-atom aligned; fewest tiles first, the
+  // taller tile on ties (less A traffic).  The choice depends on the image size only (batch invariance).
+  static int patch_env = -1, cta2_env = -1;
+  if (patch_env < 0) { const char* e = getenv("DVID_CONV_PATCH"); patch_env = e ? atoi(e) : 0; }
+  if (cta2_env < 0) { const char* e = getenv("DVID_CONV_CTA2"); cta2_env = e ? atoi(e) : 1; }
+  // (with CTA pairs enabled the 256-wide layers go to them: the patch walk has no deeper ring to offer at that width)
+  const bool patch = patch_env && R == 3 && S == 3 && stride == 1 && pad == 1 && out != nullptr && resid == nullptr &&
+                     a_strides_bytes == nullptr && (!cta2_env || cout < 256);
+  if (patch) {
+    best_tiles = -1;
+    for (int l2 = 5; l2 >= 3; --l2) {                 // (th, tw) = (4, 32), (8, 16), (16, 8)
+      const int tw = 1 << l2, th = 128 >> l2;
+      const long long t = static_cast<long long>((p.w_out + tw - 1) / tw) * ((p.h_out + th - 1) / th);
+      if (best_tiles < 0 || t <= best_tiles) { best_tiles = t; best_log2 = l2; }
+    }
+  }
   p.tw_log2 = best_log2;
   p.th = 128 >> best_log2;
   const int tw = 1 << best_log2;
@@ -986,7 +1150,13 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   }
   p.sk_ws = nullptr;
   p.sk_flags = nullptr;
+  p.patch_row_bytes = tw * 128;
+  p.patch_bytes = (p.th + 2) * tw * 128;
 
+  // CTA pairs (ConvGemmCfg): plain 256-wide convolutions with K deep enough for the ring to matter
+  // (measured per layer, tools/bench_conv_patch.py: -5..-9 % from 16 k-blocks up, +5 % at 8)
+  const bool cta2 = cta2_env && !patch && bn == 256 && out != nullptr && resid == nullptr && p.splits == 1 &&
+                    p.total_kb >= 16 && p.m_tiles >= 2 && p.trace == nullptr && p.dbg == 0;
   CUtensorMap tmA, tmB, tmC;
   {
     const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
@@ -994,7 +1164,7 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     if (a_strides_bytes != nullptr) {   // overlapping-window view (stem convolution), see stem_conv_launch
       for (int i = 0; i < 3; ++i) strides[i] = a_strides_bytes[i];
     }
-    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(tw * stride), (uint32_t)(p.th * stride), 1};
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)(tw * stride), (uint32_t)((patch ? p.th + 2 : p.th) * stride), 1};
     const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     int r = make_tmap_f16(&tmA, in, 4, dims, strides, box, es);
     if (r) return r;
@@ -1003,7 +1173,7 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     const uint64_t ktot = (uint64_t)R * S * cin;
     const uint64_t dims[2] = {ktot, (uint64_t)cout};
     const uint64_t strides[1] = {ktot * 2};
-    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)bn};
+    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)(cta2 ? bn / 2 : bn)};
     int r = make_tmap_f16(&tmB, weight, 2, dims, strides, box, nullptr);
     if (r) return r;
   }
@@ -1017,6 +1187,13 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   } else {
     if (out_f32 == nullptr) return DVID_ERR_SHAPE;
     tmC = tmA;  // unused by the fp32 path
+  }
+  if (cta2) return launch_pair(tmA, tmB, tmC, p, stream);
+  if (patch) {
+    if (p.splits != 1 || p.patch_bytes > A_PATCH_BYTES) return DVID_ERR_SHAPE;
+    if (bn == 256) return launch_cfg<256, false, false, false, true>(tmA, tmB, tmC, tmC, p, stream);
+    if (bn == 128) return launch_cfg<128, false, false, false, true>(tmA, tmB, tmC, tmC, p, stream);
+    return launch_cfg<64, false, false, false, true>(tmA, tmB, tmC, tmC, p, stream);
   }
   // weight-stationary walk when the whole K fits (<= 256) and every CTA gets several tiles of the same weight tile
   static int bstat_env = -1;
