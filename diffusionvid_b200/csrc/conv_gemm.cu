@@ -426,7 +426,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          trace_ev(p, 0, tn, (tile << 8) | kb);     // slot free, load issued
+          if (!(p.dbg & 256)) trace_ev(p, 0, tn, (tile << 8) | kb);     // slot free, load issued
           if (CTA2) {
             // the leader's barrier counts the bytes of both CTAs; each CTA brings its own A rows and half of the B rows
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
@@ -595,6 +595,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         gb += nchunks;
       }
       int done = 0;
+      int stn = 0;
       gb = 0;
       for (Walk wk = walk_begin(); walk_valid(wk); walk_next(wk)) {
         if (SK && wk.head) continue;
@@ -607,12 +608,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nchunks = min(BN / 64, (p.cout - n_idx * BN + 63) / 64);
         for (int c = (gb + sg) & 1; c < nchunks; c += 2) {
           named_bar_sync(BAR_FULL0 + sg, 160);
+          // DVID_DBG=256 + DVID_TRACE: store warp 0 logs (chunk handed over / store issued / buffer read) in the load lane
+          if ((p.dbg & 256) && sg == 0 && lane == 0) trace_ev(p, 0, stn, (tile << 8) | 0x10 | c);
           if (lane == 0 && !(p.dbg & 1)) {
             tma_store_4d(&tmC, sOut + sg * OUT_STAGE_BYTES, n_idx * BN + c * 64, x0, y0, img);
             tma_store_commit();
           }
+          if ((p.dbg & 256) && sg == 0 && lane == 0) trace_ev(p, 0, stn, (tile << 8) | 0x20 | c);
           if (++done < mine) {                    // the group will stage another chunk into this buffer
             if (lane == 0) tma_store_wait_read<0>();
+            if ((p.dbg & 256) && sg == 0 && lane == 0) trace_ev(p, 0, stn, (tile << 8) | 0x30 | c);
             __syncwarp();
             named_bar_arrive(BAR_FREE0 + sg, 160);
           }
@@ -770,8 +775,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int q = 0; q < 16; ++q) pk[q] = __ldcg(parked + (c * 16 + q) * BLOCK_M + row);
           }
-          // the store warp has drained the TMA store that last read this group's staging buffer
-          if (staged > 0) named_bar_sync(BAR_FREE0 + grp, 160);
           tmem_ld_wait();
           if (SK && sk_fin) {
 #pragma unroll
@@ -783,6 +786,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               vv[3] = __float_as_uint(__uint_as_float(vv[3]) + pk[q].w);
             }
           }
+          // The whole chunk is converted into registers BEFORE waiting for the staging buffer: the store warp hands the
+          // buffer back only after the TMA store has read it (~0.6 us behind the hand-over in the device trace, the TMA unit
+          // is busy with the operand loads), and that wait used to sit in front of the arithmetic.
+          uint4 packed[8];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float f[32];
@@ -819,10 +826,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 h2[e] = __floats2half2_rn(f[q * 8 + 2 * e], f[q * 8 + 2 * e + 1]);
                 if (p.relu == 1) h2[e] = __hmax2(h2[e], zero2);   // ReLU commutes with the rounding to fp16
               }
-              const int chunk = h * 4 + q;  // 16-byte chunk inside the 128-byte row
-              *reinterpret_cast<uint4*>(buf + row * 128 + ((chunk ^ (row & 7)) << 4)) = *reinterpret_cast<uint4*>(h2);
+              packed[h * 4 + q] = *reinterpret_cast<uint4*>(h2);
             }
           }
+          // the store warp has drained the TMA store that last read this group's staging buffer
+          if (staged > 0) named_bar_sync(BAR_FREE0 + grp, 160);
+#pragma unroll
+          for (int chunk = 0; chunk < 8; ++chunk)   // 16-byte chunk inside the 128-byte row
+            *reinterpret_cast<uint4*>(buf + row * 128 + ((chunk ^ (row & 7)) << 4)) = packed[chunk];
           fence_proxy_async_smem();
           named_bar_arrive(BAR_FULL0 + grp, 160);   // hand the staged chunk to the store warp, do not wait for it
           ++staged;
