@@ -184,6 +184,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BN, BSTAT, RES, PATCH, CTA2>;
   static_assert(!CTA2 || !SK, "no stream-K for CTA pairs");
+  // residual added in the epilogue registers (FPN top-down adds, 64-wide tiles): not compiled into the 256-wide
+  // variants, whose epilogue keeps two chunks of accumulator columns in flight and has no registers to spare for it -
+  // the host sends such layers to the 128-wide tile
+  constexpr bool ERES = !RES && BN < 256;
   const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs of the pair)
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NBAR = Cfg::NBAR;
@@ -673,7 +677,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int c_first = (gbase + grp) & 1;   // first chunk of this tile that belongs to this group
 
       const __half* rrow = nullptr;   // this thread's residual row (channel 0)
-      if (!RES && p.resid != nullptr && valid) {
+      if (ERES && p.resid != nullptr && valid) {
         rrow = p.resid + ((static_cast<long long>(img) * p.resid_h + (y >> p.resid_shift)) * p.resid_w +
                           (x >> p.resid_shift)) * p.cout;
       }
@@ -687,7 +691,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                          : make_uint4(0, 0, 0, 0);
         }
       };
-      if (!RES && p.resid != nullptr && c_first < nchunks && !sk_park) fetch_resid(c_first);
+      if (ERES && p.resid != nullptr && c_first < nchunks && !sk_park) fetch_resid(c_first);
 
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -759,17 +763,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (et == 0) trace_ev(p, 2, tn, (tile << 8) | 0xfc);   // parked tile of CTA b-1 visible
           parked = reinterpret_cast<const float4*>(p.sk_ws) + static_cast<size_t>(blockIdx.x - 1) * (BN / 4) * BLOCK_M;
         }
+        // the accumulator columns of the group's NEXT chunk are requested as soon as the current chunk is converted, so
+        // the TMEM load latency runs under the staging-buffer wait, the shared-memory stores and the hand-over
+        uint32_t v[2][32];
+        if (c_first < nchunks) {
+          tmem_ld32(tbase + c_first * 64, v[0]);
+          tmem_ld32(tbase + c_first * 64 + 32, v[1]);
+        }
 #pragma unroll 1
         for (int c = c_first; c < nchunks; c += 2) {
           uint4 rcur[8];
-          if (!RES && p.resid != nullptr) {
+          if (ERES && p.resid != nullptr) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
             if (c + 2 < nchunks) fetch_resid(c + 2);
           }
-          uint32_t v[2][32];
-          tmem_ld32(tbase + c * 64, v[0]);
-          tmem_ld32(tbase + c * 64 + 32, v[1]);
           float4 pk[SK ? 16 : 1];
           if (SK && sk_fin) {                    // all 16 loads of the chunk in flight (L2 hits, written by another SM)
 #pragma unroll
@@ -801,7 +809,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[j + 2] = __uint_as_float(v[h][j + 2]) + b4.z;
               f[j + 3] = __uint_as_float(v[h][j + 3]) + b4.w;
             }
-            if (!RES && p.resid != nullptr) {
+            if (ERES && p.resid != nullptr) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const __half2* rh = reinterpret_cast<const __half2*>(&rcur[h * 4 + q]);
@@ -828,6 +836,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               packed[h * 4 + q] = *reinterpret_cast<uint4*>(h2);
             }
+          }
+          if (c + 2 < nchunks) {
+            tmem_ld32(tbase + (c + 2) * 64, v[0]);
+            tmem_ld32(tbase + (c + 2) * 64 + 32, v[1]);
           }
           // the store warp has drained the TMA store that last read this group's staging buffer
           if (staged > 0) named_bar_sync(BAR_FREE0 + grp, 160);
@@ -1139,6 +1151,7 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     if (res_same && bn == 64) bn = 128;
   }
   if (bn != 64 && bn != 128 && bn != 256) return DVID_ERR_SHAPE;
+  if (bn == 256 && resid != nullptr && !(resid_shift == 0 && out != nullptr)) bn = 128;   // epilogue residual: see ERES
   p.n_tiles = (cout + bn - 1) / bn;
   p.div_m_tiles.init(p.m_tiles);
   p.div_n_tiles.init(p.n_tiles);
