@@ -123,7 +123,7 @@ constexpr int A_PATCH_BYTES = 24 * 1024;   // (th + 2) * tw * 128 <= 24 KB: (th,
 template <int BN, bool BSTAT = false, bool RES = false, bool PATCH = false, bool CTA2 = false>
 struct ConvGemmCfg {
   static constexpr int B_STAGE_BYTES = (CTA2 ? BN / 2 : BN) * BLOCK_K * 2;
-  static constexpr int STAGES0 = CTA2 ? 6 : (BSTAT ? ((BN == 256) ? 4 : 6) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8)));
+  static constexpr int STAGES0 = CTA2 ? 6 : (BSTAT ? ((BN == 256) ? 4 : 8) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8)));
   static constexpr int STAGES = STAGES0 - (RES ? 1 : 0);   // room for the identity tile (and keeps BN=256 under 227 KB)
   static constexpr int PA = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);   // A patch stages
   static constexpr int PB = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);   // B tile stages
@@ -1152,6 +1152,15 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
   }
   if (bn != 64 && bn != 128 && bn != 256) return DVID_ERR_SHAPE;
   if (bn == 256 && resid != nullptr && !(resid_shift == 0 && out != nullptr)) bn = 128;   // epilogue residual: see ERES
+  // K <= 256 with a tensor-core residual (bottleneck conv3 of res2..res4): the four residual chunks of a 256-wide tile
+  // queue behind its four k-blocks in a THREE-stage ring (128 KB of resident weights leave no room for more) and the
+  // device trace shows 2.2 us per tile between the last k-block and the finished accumulator; the 128-wide tile has a
+  // five-stage ring: 26.4 -> 24.6 us (res4), 39.4 -> 36.0 (res3), 64.8 -> 60.0 (res2), tools/bench_conv_res.py
+  if (bn == 256 && res_same && p.total_kb <= BSTAT_MAX_KB && force_bn == 0) {
+    static int env_forced = -1;
+    if (env_forced < 0) { const char* e = getenv("DVID_FORCE_BN"); env_forced = (e && atoi(e) > 0) ? 1 : 0; }
+    if (!env_forced) bn = 128;
+  }
   p.n_tiles = (cout + bn - 1) / bn;
   p.div_m_tiles.init(p.m_tiles);
   p.div_n_tiles.init(p.n_tiles);
