@@ -125,19 +125,21 @@ struct ConvGemmCfg {
   static constexpr int B_STAGE_BYTES = (CTA2 ? BN / 2 : BN) * BLOCK_K * 2;
   static constexpr int STAGES0 = CTA2 ? 6 : (BSTAT ? ((BN == 256) ? 4 : 8) : ((BN == 256) ? 4 : ((BN == 128) ? 6 : 8)));
   static constexpr int STAGES = STAGES0 - (RES ? 1 : 0);   // room for the identity tile (and keeps BN=256 under 227 KB)
-  static constexpr int PA = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);   // A patch stages
-  static constexpr int PB = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);   // B tile stages
+  // ring depth in k-blocks is what the saved A bytes buy: 3 * PA and PB k-blocks in flight (plain walk: 4 / 6 / 8)
+  static constexpr int PA = (BN == 256) ? 2 : ((BN == 128) ? 3 : 4);   // A patch stages (24 KB each)
+  static constexpr int PB = (BN == 256) ? 4 : ((BN == 128) ? 7 : 12);  // B tile stages
   static constexpr int NBAR = PATCH ? (PA + PB) : STAGES;              // full / empty barrier pairs of the rings
+  static constexpr int CTL_BYTES = PATCH ? 384 : 256;                  // mbarriers + TMEM slot
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int RING_BYTES =
       PATCH ? (PA * A_PATCH_BYTES + PB * B_STAGE_BYTES)
             : (BSTAT ? (STAGES * A_STAGE_BYTES + BSTAT_MAX_KB * B_STAGE_BYTES) : (STAGES * (A_STAGE_BYTES + B_STAGE_BYTES)));
-  static constexpr int SMEM_BYTES = RING_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+  static constexpr int SMEM_BYTES = RING_BYTES + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + CTL_BYTES /*barriers*/ +
                                     (BN * 4 > 512 ? BN * 4 : 512) /*bias staging: each epilogue group its own half*/ +
                                     (RES ? IDENT_BYTES : 0);
   static_assert(!PATCH || (!BSTAT && !RES), "the column-patch walk serves the plain variants only");
   static_assert(!CTA2 || (!BSTAT && !RES && !PATCH && BN == 256), "CTA pairs serve the plain 256-wide variant only");
-  static_assert(2 * NBAR * 8 + 6 * 8 + 4 <= 256, "barrier block");
+  static_assert(2 * NBAR * 8 + 6 * 8 + 4 <= CTL_BYTES, "barrier block");
 };
 
 // GELU, erf form (torch.nn.GELU default; Swin MLP, swintransformer.py:47-66): x * Phi(x).  erff() costs ~30
@@ -210,7 +212,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* bres_full = tmem_empty + 2;           // BSTAT: resident weights landed / may be overwritten
   uint64_t* bres_empty = bres_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_empty + 1);
-  float* sBias = reinterpret_cast<float*>(sCtl + 256);   // [BN] bias of the current tile
+  float* sBias = reinterpret_cast<float*>(sCtl + Cfg::CTL_BYTES);   // [BN] bias of the current tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
