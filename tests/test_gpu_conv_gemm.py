@@ -230,3 +230,26 @@ def test_conv_stream_k_schedule(cuda, streamk, n, h, w, cin, cout, R, topdown):
     _lib.check(_lib.lib().dvid_conv_streamk(1), "dvid_conv_streamk")
     assert (first.float() - plain.float()).abs().max().item() <= 1e-3 * scale
     assert torch.equal(run(), first)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,R,stride", [
+    (9, 38, 64, 256, 256, 3, 1),      # 171 M tiles: odd, the last pair has an out-of-range partner tile
+    (8, 38, 64, 256, 384, 3, 1),      # second N tile half empty: the peer CTA's half of the weight rows is out of range
+    (8, 76, 128, 256, 256, 3, 2),     # stride 2 (res4.0 conv2)
+    (8, 19, 32, 2048, 512, 1, 1),     # 1x1, 32 k-blocks, 40 M tiles x 2 N tiles
+    (8, 37, 61, 256, 256, 3, 1),      # ragged image: tile tails in x and y
+])
+def test_conv_cta_pair_variant(cuda, n, h, w, cin, cout, R, stride):
+    """Shapes that take the cta_group::2 pair variant of the conv kernel (plain 256-wide tiles, >= 16 k-blocks; default
+    on, DVID_CONV_CTA2=0 switches it off): pairs of adjacent M tiles, each CTA loading half of the weight rows."""
+    g = torch.Generator(device="cpu").manual_seed(n * 100 + cout + R)
+    x = torch.randn(n, h, w, cin, generator=g).half().to(cuda)
+    wt = (torch.randn(cout, R, R, cin, generator=g) / (cin * R * R) ** 0.5).half().to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias,
+                                                stride=stride, padding=R // 2)).permute(0, 2, 3, 1)
+    out = _conv(x, wt.view(cout, -1), bias, None, cout, R, R, stride, R // 2, 0, 1)
+    assert not torch.isnan(out).any()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
+    assert torch.equal(_conv(x, wt.view(cout, -1), bias, None, cout, R, R, stride, R // 2, 0, 1), out)
