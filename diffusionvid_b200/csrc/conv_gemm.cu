@@ -1132,6 +1132,9 @@ int conv_gemm_launch(const void* in, const void* weight, const float* bias, cons
     // (tools/bench_gemm.py with DVID_FORCE_BN): a 128-wide tile costs ~0.78 of a 256-wide one (the A tile is re-read
     // from smem per MMA, same epilogue overheads), a 64-wide one ~0.55.  Example: res5 3x3 conv, 38 M tiles x 512
     // channels: bn=256 -> 1 wave x 1.0 (37.9 us), bn=128 -> 2 waves x 0.78 (52.2 us).
+    // (Round-2 device traces explain the costs: an M=128 x K=16 MMA occupies the tensor pipe for ~130 cycles whatever its
+    // N, so a k-block of a 64-wide tile takes as long as one of a 256-wide tile - 0.27-0.3 us - and only the epilogue and
+    // the bytes per k-block shrink with the width.)
     const double tile_cost[3] = {1.0, 0.78, 0.55};
     const int cand[3] = {256, 128, 64};
     double best = 1e30;
